@@ -1,0 +1,145 @@
+/*
+ * smcpp_b200 -- C ABI of the B200-native E-step of SMC++ (libsmcpp_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point names
+ * the piece of the reference (popgenmethods/smcpp @ 6779faec) that it replaces; INTEGRATION.md shows the
+ * host-side binding a maintainer adds to the reference's InferenceManager to call it.
+ *
+ * One context drives ONE GPU (one process per GPU, or several contexts in one process).  Contigs are
+ * independent HMMs (reference src/inference_manager.cpp:89-94), so a multi-GPU run gives every context
+ * its shard of the contigs and sums the packed statistics (`reduced`) with one all-reduce.
+ *
+ * All matrices cross this boundary ROW-major, X[i*M + j] = X(i, j) (what NumPy and the reference's
+ * store_matrix(), src/common.cpp:8-11, produce).  All functions return 0 on success; on failure they
+ * return non-zero and smcpp_b200_last_error() describes it.  Nothing here throws or calls back into the
+ * host language, and everything may be called with the Python GIL released (the reference calls Estep
+ * under `with nogil`, smcpp/_smcpp.pyx:189-190, declared without `except +`, smcpp/_smcpp.pxd:49).
+ * There is no CPU fallback: without a usable CUDA device create() fails.
+ */
+#ifndef SMCPP_B200_H
+#define SMCPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smcpp_b200_ctx smcpp_b200_ctx;
+
+/* ABI version of this header (bumped on any signature change). */
+int smcpp_b200_abi_version(void);
+
+/* Create / destroy a context bound to CUDA device `device`.
+ * Replaces: nothing in the reference (it has no device); lifetime = the InferenceManager's. */
+int smcpp_b200_create(smcpp_b200_ctx **out, int device);
+void smcpp_b200_destroy(smcpp_b200_ctx *ctx);
+const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx); /* ctx may be NULL: error of the last failed create() */
+
+/* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks", "target_warps", "fwd_tol",
+ * "bwd_tol", "max_sweeps", "force_sequential"}.  Returns non-zero for an unknown name. */
+int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value);
+
+/*
+ * One-time upload of the observations of this context's contigs.
+ * Replaces: InferenceManager::InferenceManager / map_obs / fill_targets / populate_emission_probs
+ *           (reference src/inference_manager.cpp:21-54, 180-188, 232-254, 190-211) and HMM::HMM's
+ *           bookkeeping (src/hmm.cpp:8-28).
+ *   obs[c]    int32 row-major [lengths[c]][1 + 3*npop], rows [span, a_1, b_1, nb_1 (, a_2, b_2, nb_2)];
+ *             only read during this call (the reference keeps the pointers; we copy to the device).
+ *   keys      optional global key table [n_keys][3*npop] in the reference's std::map order
+ *             (lexicographic, include/block_key.h:51-60); NULL = derive it from these contigs.  A key
+ *             of the data that is missing from an explicit table is an error.  Multi-GPU runs pass
+ *             the union over all shards so every context packs gamma_sums identically.
+ * Errors: span <= 0 -> "data are malformed: span <= 0" (reference src/inference_manager.cpp:243-244).
+ */
+int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *const *obs,
+                           const int32_t *lengths, int npop, const int32_t *keys, int n_keys);
+
+/* Key universe after set_contigs(): K, the K x 3*npop table, which keys occur with span > 1
+ * (the reference's eigensystem targets, src/inference_manager.cpp:245-246) and, per contig, which
+ * keys occur at all (the reference's gamma_sums maps hold exactly those, src/hmm.cpp:51-53,69). */
+int smcpp_b200_num_keys(const smcpp_b200_ctx *ctx);
+int smcpp_b200_get_keys(const smcpp_b200_ctx *ctx, int32_t *keys /* K*3P */);
+int smcpp_b200_num_eig_keys(const smcpp_b200_ctx *ctx);
+int smcpp_b200_get_eig_keys(const smcpp_b200_ctx *ctx, int32_t *key_idx /* n_eig */);
+int smcpp_b200_get_key_present(const smcpp_b200_ctx *ctx, uint8_t *present /* C*K */);
+int64_t smcpp_b200_total_blocks(const smcpp_b200_ctx *ctx);
+
+/*
+ * Eigensystems of diag(e_key) * Td^T for the keys returned by get_eig_keys(), computed by the library
+ * (real non-symmetric QR algorithm, real parts kept like the reference).
+ * Replaces: the EigenSolver loop of TransitionBundle::update (reference src/transition_bundle.cpp:14-25)
+ *           and struct eigensystem (include/transition_bundle.h:9-30).
+ * Outputs [n_eig][M][M] / [n_eig][M] / [n_eig]; cplx[e] != 0 when an eigenvalue had an imaginary part.
+ */
+int smcpp_b200_eigensystems(smcpp_b200_ctx *ctx, int M, const double *T, const double *E /* K*M */,
+                            double *P, double *Pinv, double *d, double *d_scaled, double *scale, int32_t *cplx);
+
+/* Context-free forms of the same host routine (usable without a GPU; the unit tests call these):
+ * one general real matrix A[n][n] -> P, Pinv (real parts), Re(d), Im(d); and the per-key batch. */
+int smcpp_b200_host_eig(int n, const double *A, double *P, double *Pinv, double *d_re, double *d_im);
+int smcpp_b200_host_eigensystems(int M, int K, int n_eig, const int32_t *eig_key_idx, const double *T,
+                                 const double *E, double *P, double *Pinv, double *d, double *d_scaled,
+                                 double *scale, int32_t *cplx);
+
+/*
+ * One E-step over all contigs of this context.
+ * Replaces: InferenceManager::Estep -> TransitionBundle::update(T, true) -> parallel_do(HMM::Estep)
+ *           (reference src/inference_manager.cpp:108-114, src/transition_bundle.cpp:3-61,
+ *           src/hmm.cpp:45-153), with pi / T / emission table as do_dirty_work() leaves them (:213-229).
+ * Inputs (host pointers):
+ *   pi[M], T[M][M] (value part of the transition), E[K][M] (emission_probs in key order),
+ *   n_eig eigensystems in the order of get_eig_keys(): P, Pinv [n_eig][M][M], d, d_scaled [n_eig][M],
+ *   scale [n_eig]; pass P == NULL to have the library compute them (smcpp_b200_eigensystems).
+ * Outputs (host pointers, caller-owned; any may be NULL):
+ *   ll[C]                 HMM::ll
+ *   xisum[C][M][M]        HMM::xisum   (after the final "o Td" and 1e-20 floor, src/hmm.cpp:151-152)
+ *   gamma0[C][M]          HMM::gamma.col(0)
+ *   gamma_sums[C][K][M]   HMM::gamma_sums, zero rows for keys absent from the contig
+ *   reduced[1+M+M*M+K*M]  sum over this context's contigs of [ll | gamma0 | xisum | gamma_sums]
+ *                         (the all-reduce payload of a multi-GPU run; reference Q() is linear in it)
+ */
+int smcpp_b200_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E,
+                     int n_eig, const double *P, const double *Pinv, const double *d, const double *d_scaled,
+                     const double *scale, double *ll, double *xisum, double *gamma0, double *gamma_sums,
+                     double *reduced);
+
+/* Device pointer (on this context's GPU) to the packed `reduced` vector of the last estep(), length
+ * 1 + M + M*M + K*M doubles, valid until the next estep(); lets the caller all-reduce it in place. */
+int smcpp_b200_reduced_device_ptr(smcpp_b200_ctx *ctx, void **ptr, int64_t *count);
+
+/* Same E-step, but nothing is copied back to the host: results stay in the device buffers (per-contig
+ * outputs and `reduced`).  Used to time the kernels alone; follow with smcpp_b200_fetch() for values. */
+int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E,
+                            int n_eig, const double *P, const double *Pinv, const double *d,
+                            const double *d_scaled, const double *scale, int upload_inputs);
+int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums,
+                     double *reduced);
+
+/* Diagnostics of the last estep(): see smcpp_b200_stats_t. */
+typedef struct smcpp_b200_stats_t {
+    int32_t n_chunks;        /* chunks the contigs were split into */
+    int32_t chunk_blocks;    /* blocks per chunk */
+    int32_t burn_in_blocks;  /* burn-in length used for chunk boundaries */
+    int32_t fwd_sweeps;      /* forward passes executed (1 = burn-in accepted everywhere) */
+    int32_t bwd_sweeps;
+    int32_t fwd_redone;      /* chunks re-run because the boundary check failed */
+    int32_t bwd_redone;
+    int32_t kernel_launches; /* CUDA kernels launched by the last estep() */
+    float ms_setup, ms_forward, ms_backward, ms_stats, ms_finalize, ms_total; /* CUDA-event times */
+    double fwd_max_mismatch, bwd_max_mismatch;
+} smcpp_b200_stats_t;
+int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out);
+
+/* CUDA stream handle (cudaStream_t) the context launches on, for event timing by the caller. */
+int smcpp_b200_stream(smcpp_b200_ctx *ctx, void **stream);
+
+/* Debug/verification taps (used by tests): copy out the stored float alpha_hat columns of one contig,
+ * [L+1][M], as the reference's HMM::alpha_hat (include/hmm.h:35) would hold them. */
+int smcpp_b200_debug_alpha_hat(smcpp_b200_ctx *ctx, int contig, float *out /* (L+1)*M */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCPP_B200_H */

@@ -1,0 +1,250 @@
+"""ctypes binding of libsmcpp_b200.so (the C ABI declared in include/smcpp_b200.h).
+
+The library is the product: if it cannot be loaded, or no CUDA device is usable, every entry point
+raises -- there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmcpp_b200.so")
+_lib = None
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n_chunks", ctypes.c_int32), ("chunk_blocks", ctypes.c_int32), ("burn_in_blocks", ctypes.c_int32),
+                ("fwd_sweeps", ctypes.c_int32), ("bwd_sweeps", ctypes.c_int32), ("fwd_redone", ctypes.c_int32),
+                ("bwd_redone", ctypes.c_int32), ("kernel_launches", ctypes.c_int32),
+                ("ms_setup", ctypes.c_float), ("ms_forward", ctypes.c_float), ("ms_backward", ctypes.c_float),
+                ("ms_stats", ctypes.c_float), ("ms_finalize", ctypes.c_float), ("ms_total", ctypes.c_float),
+                ("fwd_max_mismatch", ctypes.c_double), ("bwd_max_mismatch", ctypes.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/smcpp_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = [
+    "smcpp_b200_abi_version", "smcpp_b200_create", "smcpp_b200_destroy", "smcpp_b200_last_error",
+    "smcpp_b200_set_option", "smcpp_b200_set_contigs", "smcpp_b200_num_keys", "smcpp_b200_get_keys",
+    "smcpp_b200_num_eig_keys", "smcpp_b200_get_eig_keys", "smcpp_b200_get_key_present", "smcpp_b200_total_blocks",
+    "smcpp_b200_eigensystems", "smcpp_b200_host_eig", "smcpp_b200_host_eigensystems", "smcpp_b200_estep",
+    "smcpp_b200_reduced_device_ptr", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
+    "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat",
+]
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src))
+    newest = max(newest, os.path.getmtime(os.path.join(_HERE, "..", "include", "smcpp_b200.h")))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.check_call(["make", "-s", "-C", src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(smcpp_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.smcpp_b200_last_error.restype = ctypes.c_char_p
+        L.smcpp_b200_last_error.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_total_blocks.restype = ctypes.c_int64
+        L.smcpp_b200_total_blocks.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_destroy.restype = None
+        L.smcpp_b200_destroy.argtypes = [ctypes.c_void_p]
+        for name in ("smcpp_b200_num_keys", "smcpp_b200_num_eig_keys"):
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def ptr(a, t):
+    if a is None:
+        return None
+    return a.ctypes.data_as(t)
+
+
+def host_eig(A: np.ndarray):
+    """Eigen-decomposition of a general real matrix by the library's host routine -> (P, Pinv, d_re, d_im)."""
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    P = np.empty((n, n)); Pi = np.empty((n, n)); dr = np.empty(n); di = np.empty(n)
+    rc = lib().smcpp_b200_host_eig(ctypes.c_int(n), ptr(A, c_f64p), ptr(P, c_f64p), ptr(Pi, c_f64p), ptr(dr, c_f64p),
+                                   ptr(di, c_f64p))
+    if rc:
+        raise RuntimeError("smcpp_b200_host_eig failed")
+    return P, Pi, dr, di
+
+
+def host_eigensystems(T: np.ndarray, E: np.ndarray, eig_key_idx: np.ndarray) -> dict:
+    T = np.ascontiguousarray(T, np.float64); E = np.ascontiguousarray(E, np.float64)
+    idx = np.ascontiguousarray(eig_key_idx, np.int32)
+    M, K, ne = T.shape[0], E.shape[0], idx.shape[0]
+    out = {"eig_key_idx": idx, "eig_P": np.empty((ne, M, M)), "eig_Pinv": np.empty((ne, M, M)), "eig_d": np.empty((ne, M)),
+           "eig_dscaled": np.empty((ne, M)), "eig_scale": np.empty(ne), "eig_cplx": np.zeros(ne, np.int32)}
+    rc = lib().smcpp_b200_host_eigensystems(ctypes.c_int(M), ctypes.c_int(K), ctypes.c_int(ne), ptr(idx, c_i32p),
+                                            ptr(T, c_f64p), ptr(E, c_f64p), ptr(out["eig_P"], c_f64p),
+                                            ptr(out["eig_Pinv"], c_f64p), ptr(out["eig_d"], c_f64p),
+                                            ptr(out["eig_dscaled"], c_f64p), ptr(out["eig_scale"], c_f64p),
+                                            ptr(out["eig_cplx"], c_i32p))
+    if rc:
+        raise RuntimeError("smcpp_b200_host_eigensystems failed")
+    return out
+
+
+class Context:
+    """One GPU's E-step engine (thin, typed view of the C ABI)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        rc = lib().smcpp_b200_create(ctypes.byref(self._h), ctypes.c_int(device))
+        if rc:
+            raise RuntimeError("smcpp_b200_create: " + lib().smcpp_b200_last_error(None).decode())
+        self.C = 0
+        self.K = 0
+        self.M = 0
+
+    def close(self):
+        if self._h:
+            lib().smcpp_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: " + lib().smcpp_b200_last_error(self._h).decode())
+
+    def set_option(self, name: str, value: float):
+        self._check(lib().smcpp_b200_set_option(self._h, name.encode(), ctypes.c_double(value)), "set_option")
+
+    def set_contigs(self, contigs, npop: int, keys: np.ndarray | None = None):
+        arrs = [np.ascontiguousarray(c, np.int32) for c in contigs]
+        W = 1 + 3 * npop
+        for a in arrs:
+            if a.ndim != 2 or a.shape[1] != W:
+                raise ValueError(f"observations must be [L, {W}] int32")
+        C = len(arrs)
+        ptrs = (c_i32p * C)(*[ptr(a, c_i32p) for a in arrs])
+        lens = np.asarray([a.shape[0] for a in arrs], np.int32)
+        kp, nk = None, 0
+        if keys is not None:
+            keys = np.ascontiguousarray(keys, np.int32)
+            kp, nk = ptr(keys, c_i32p), keys.shape[0]
+        self._check(lib().smcpp_b200_set_contigs(self._h, ctypes.c_int(C), ptrs, ptr(lens, c_i32p), ctypes.c_int(npop),
+                                                 kp, ctypes.c_int(nk)), "set_contigs")
+        self.C, self.npop = C, npop
+        self.K = lib().smcpp_b200_num_keys(self._h)
+        self.lengths = lens
+
+    @property
+    def keys(self) -> np.ndarray:
+        k = np.empty((self.K, 3 * self.npop), np.int32)
+        self._check(lib().smcpp_b200_get_keys(self._h, ptr(k, c_i32p)), "get_keys")
+        return k
+
+    @property
+    def eig_keys(self) -> np.ndarray:
+        n = lib().smcpp_b200_num_eig_keys(self._h)
+        k = np.empty(n, np.int32)
+        if n:
+            self._check(lib().smcpp_b200_get_eig_keys(self._h, ptr(k, c_i32p)), "get_eig_keys")
+        return k
+
+    @property
+    def key_present(self) -> np.ndarray:
+        p = np.empty((self.C, self.K), np.uint8)
+        self._check(lib().smcpp_b200_get_key_present(self._h, ptr(p, c_u8p)), "get_key_present")
+        return p
+
+    @property
+    def total_blocks(self) -> int:
+        return int(lib().smcpp_b200_total_blocks(self._h))
+
+    def _eig_args(self, eig):
+        if eig is None:
+            return 0, None, None, None, None, None, []
+        keep = [np.ascontiguousarray(eig[k], np.float64) for k in ("eig_P", "eig_Pinv", "eig_d", "eig_dscaled", "eig_scale")]
+        return (keep[0].shape[0], ptr(keep[0], c_f64p), ptr(keep[1], c_f64p), ptr(keep[2], c_f64p), ptr(keep[3], c_f64p),
+                ptr(keep[4], c_f64p), keep)
+
+    def estep(self, pi, T, E, eig: dict | None = None) -> dict:
+        """One E-step.  `eig` = dict with eig_P, eig_Pinv, eig_d, eig_dscaled, eig_scale in the order of
+        self.eig_keys (e.g. the reference's own eigensystems), or None to let the library compute them."""
+        pi = np.ascontiguousarray(pi, np.float64); T = np.ascontiguousarray(T, np.float64)
+        E = np.ascontiguousarray(E, np.float64)
+        M, K, C = pi.shape[0], self.K, self.C
+        if E.shape != (K, M) or T.shape != (M, M):
+            raise ValueError("shape mismatch: T must be [M,M], E must be [K,M]")
+        ne, pP, pPi, pd, pds, psc, keep = self._eig_args(eig)
+        out = {"ll": np.empty(C), "xisum": np.empty((C, M, M)), "gamma0": np.empty((C, M)),
+               "gamma_sums": np.empty((C, K, M)), "reduced": np.empty(1 + M + M * M + K * M)}
+        self._check(lib().smcpp_b200_estep(self._h, ctypes.c_int(M), ptr(pi, c_f64p), ptr(T, c_f64p), ptr(E, c_f64p),
+                                           ctypes.c_int(ne), pP, pPi, pd, pds, psc, ptr(out["ll"], c_f64p),
+                                           ptr(out["xisum"], c_f64p), ptr(out["gamma0"], c_f64p),
+                                           ptr(out["gamma_sums"], c_f64p), ptr(out["reduced"], c_f64p)), "estep")
+        self.M = M
+        out["key_present"] = self.key_present
+        return out
+
+    def estep_device(self, pi, T, E, eig: dict | None = None, upload: bool = True):
+        pi = np.ascontiguousarray(pi, np.float64); T = np.ascontiguousarray(T, np.float64)
+        E = np.ascontiguousarray(E, np.float64)
+        M = pi.shape[0]
+        ne, pP, pPi, pd, pds, psc, keep = self._eig_args(eig)
+        self._check(lib().smcpp_b200_estep_device(self._h, ctypes.c_int(M), ptr(pi, c_f64p), ptr(T, c_f64p),
+                                                  ptr(E, c_f64p), ctypes.c_int(ne), pP, pPi, pd, pds, psc,
+                                                  ctypes.c_int(1 if upload else 0)), "estep_device")
+        self.M = M
+
+    def fetch(self) -> dict:
+        M, K, C = self.M, self.K, self.C
+        out = {"ll": np.empty(C), "xisum": np.empty((C, M, M)), "gamma0": np.empty((C, M)),
+               "gamma_sums": np.empty((C, K, M)), "reduced": np.empty(1 + M + M * M + K * M)}
+        self._check(lib().smcpp_b200_fetch(self._h, ptr(out["ll"], c_f64p), ptr(out["xisum"], c_f64p),
+                                           ptr(out["gamma0"], c_f64p), ptr(out["gamma_sums"], c_f64p),
+                                           ptr(out["reduced"], c_f64p)), "fetch")
+        return out
+
+    def reduced_device_ptr(self):
+        p = ctypes.c_void_p(); n = ctypes.c_int64()
+        self._check(lib().smcpp_b200_reduced_device_ptr(self._h, ctypes.byref(p), ctypes.byref(n)), "reduced_device_ptr")
+        return p.value, n.value
+
+    def eigensystems(self, T, E) -> dict:
+        return host_eigensystems(T, E, self.eig_keys)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(lib().smcpp_b200_get_stats(self._h, ctypes.byref(s)), "get_stats")
+        return s.as_dict()
+
+    def stream(self) -> int:
+        p = ctypes.c_void_p()
+        self._check(lib().smcpp_b200_stream(self._h, ctypes.byref(p)), "stream")
+        return p.value or 0
+
+    def debug_alpha_hat(self, contig: int) -> np.ndarray:
+        L = int(self.lengths[contig])
+        out = np.empty((L + 1, self.M), np.float32)
+        self._check(lib().smcpp_b200_debug_alpha_hat(self._h, ctypes.c_int(contig), ptr(out, c_f32p)), "debug_alpha_hat")
+        return out

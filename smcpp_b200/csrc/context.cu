@@ -1,0 +1,771 @@
+// smcpp_b200 -- host side of the C ABI (include/smcpp_b200.h): dataset layout, chunk planning, the
+// sweep loop around the recursion kernels, staging of inputs/outputs.  No CPU fallback lives here: every
+// numeric result of estep() is produced by the kernels in estep_kernels.cu.
+#include "../../include/smcpp_b200.h"
+#include "eigen_host.h"
+#include "estep_kernels.cuh"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace smcb;
+
+namespace {
+
+std::string g_create_error;
+
+struct KeyRow {
+    std::array<int32_t, 6> v;
+    bool operator==(const KeyRow &o) const { return v == o.v; }
+};
+struct KeyRowHash {
+    size_t operator()(const KeyRow &k) const
+    {
+        uint64_t h = 1469598103934665603ull;
+        for (int32_t x : k.v) { h ^= (uint32_t)x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+template <typename T> struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct smcpp_b200_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_setup_done = nullptr, ev_bwd_done = nullptr;
+    std::string err;
+
+    // ---- dataset (set_contigs)
+    int C = 0, npop = 0, K = 0, n_eig = 0;
+    int64_t total = 0;
+    std::vector<int64_t> blk_off;
+    std::vector<int32_t> keys;        // K x 3P
+    std::vector<int32_t> eig_keys;    // n_eig key indices (ascending = the reference's map order)
+    std::vector<int32_t> eig_of_key;  // K
+    std::vector<uint8_t> present;     // C x K
+    std::vector<int32_t> h_span;
+    std::vector<uint16_t> h_key;
+    DevBuf<int32_t> d_span;
+    DevBuf<uint16_t> d_key;
+    DevBuf<int64_t> d_blk_off, d_col_off;
+    DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
+    DevBuf<uint32_t> d_sl_mask;
+    DevBuf<int> d_eig_of_key, d_key_of_eig;
+
+    // ---- options
+    int opt_chunk_blocks = 0;       // 0 = auto
+    int opt_burn_in = 512;
+    int opt_target_warps = 148 * 16;
+    int opt_slab_blocks = 2048;
+    double opt_fwd_tol = 4e-7, opt_bwd_tol = 1e-10;
+    int opt_max_sweeps = 1 << 30;
+    int opt_force_sequential = 0;
+    int burn_in_adapt = 0;          // grows when boundary checks fail (sticky between E-steps)
+
+    // ---- plan
+    bool plan_valid = false;
+    int plan_Lc = 0, plan_burn = 0, plan_slab = 0;
+    int n_chunks = 0, n_slabs = 0;
+    int64_t n_cols = 0;
+    std::vector<int32_t> chunk_off, slab_off;
+    std::vector<int64_t> col_off;
+
+    // ---- model + work buffers
+    int M = 0, Mp = 0;
+    DevBuf<double> d_in;            // staged raw inputs
+    PinBuf<double> h_in;
+    DevBuf<double> m_pi, m_Td, m_TdT, m_E, m_P, m_PT, m_Pinv, m_PinvT, m_dsc, m_logd, m_dr, m_scale, m_logscale;
+    DevBuf<float> m_A32;
+    DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
+    DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
+        w_scratch, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
+    DevBuf<uint8_t> w_fwd_flag, w_bwd_flag;
+    DevBuf<int> w_counters;
+    PinBuf<int> h_counters;
+    PinBuf<double> h_out;
+    std::vector<double> eig_store;  // library-computed eigensystems of the last estep
+
+    smcpp_b200_stats_t stats = {};
+
+    Model model() const
+    {
+        Model m;
+        m.M = M; m.Mp = Mp; m.K = K; m.n_eig = n_eig;
+        m.pi = m_pi.p; m.Td = m_Td.p; m.TdT = m_TdT.p; m.A32 = m_A32.p; m.E = m_E.p;
+        m.eig_of_key = d_eig_of_key.p; m.key_of_eig = d_key_of_eig.p;
+        m.P = m_P.p; m.PT = m_PT.p; m.Pinv = m_Pinv.p; m.PinvT = m_PinvT.p;
+        m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
+        return m;
+    }
+    Plan plan() const
+    {
+        Plan p;
+        p.n_contigs = C; p.n_chunks = n_chunks; p.n_slabs = n_slabs;
+        p.chunk_blocks = plan_Lc; p.burn_in = plan_burn; p.slab_blocks = plan_slab;
+        p.total_blocks = total;
+        p.span = d_span.p; p.key = d_key.p;
+        p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
+        p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
+        p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
+        return p;
+    }
+    Work work() const
+    {
+        Work w;
+        w.alpha = w_alpha.p; w.cnorm = w_cnorm.p; w.bvec = w_bvec.p;
+        w.start_used = w_start_used.p; w.end_alpha = w_end_alpha.p; w.end_alpha_prev = w_end_alpha_prev.p;
+        w.ll_chunk = w_ll_chunk.p; w.bstart_used = w_bstart_used.p; w.beta_out = w_beta_out.p;
+        w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p;
+        w.counters = w_counters.p;
+        w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p;
+        w.ll = o_ll.p; w.xisum = o_xisum.p; w.gamma0 = o_gamma0.p; w.gamma_sums = o_gamma_sums.p; w.reduced = o_reduced.p;
+        return w;
+    }
+};
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return 1;                                                                                 \
+        }                                                                                             \
+    } while (0)
+
+static int fail(smcpp_b200_ctx *ctx, const std::string &msg)
+{
+    ctx->err = msg;
+    return 1;
+}
+
+extern "C" {
+
+int smcpp_b200_abi_version(void) { return 1; }
+
+int smcpp_b200_create(smcpp_b200_ctx **out, int device)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                         "); smcpp_b200 has no CPU fallback";
+        return 1;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return 1;
+    }
+    smcpp_b200_ctx *ctx = new smcpp_b200_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
+        delete ctx;
+        return 1;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&ctx->ev_setup_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_bwd_done, cudaEventDisableTiming);
+    *out = ctx;
+    return 0;
+}
+
+void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    // DevBuf / PinBuf members are released explicitly (they are plain structs without destructors)
+    ctx->d_span.release(); ctx->d_key.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
+    ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
+    ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
+    ctx->d_sl_mask.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
+    ctx->d_in.release(); ctx->h_in.release();
+    ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
+    ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
+    ctx->m_dr.release(); ctx->m_scale.release(); ctx->m_logscale.release(); ctx->m_A32.release();
+    ctx->w_alpha.release(); ctx->w_cnorm.release(); ctx->w_start_used.release(); ctx->w_end_alpha.release();
+    ctx->w_end_alpha_prev.release(); ctx->w_bvec.release(); ctx->w_ll_chunk.release(); ctx->w_bstart_used.release();
+    ctx->w_beta_out.release(); ctx->w_beta_out_prev.release(); ctx->w_Xpart.release(); ctx->w_Rpart.release();
+    ctx->w_dpart.release(); ctx->w_gspart.release(); ctx->w_scratch.release(); ctx->o_ll.release();
+    ctx->o_xisum.release(); ctx->o_gamma0.release(); ctx->o_gamma_sums.release(); ctx->o_reduced.release();
+    ctx->w_fwd_flag.release(); ctx->w_bwd_flag.release(); ctx->w_counters.release(); ctx->h_counters.release();
+    ctx->h_out.release();
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_setup_done) cudaEventDestroy(ctx->ev_setup_done);
+    if (ctx->ev_bwd_done) cudaEventDestroy(ctx->ev_bwd_done);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
+    delete ctx;
+}
+
+const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
+{
+    if (!ctx || !name) return 1;
+    std::string n(name);
+    if (n == "chunk_blocks") ctx->opt_chunk_blocks = (int)value;
+    else if (n == "burn_in_blocks") { ctx->opt_burn_in = (int)value; ctx->burn_in_adapt = 0; }
+    else if (n == "target_warps") ctx->opt_target_warps = std::max(1, (int)value);
+    else if (n == "slab_blocks") ctx->opt_slab_blocks = std::max(32, (int)value);
+    else if (n == "fwd_tol") ctx->opt_fwd_tol = value;
+    else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
+    else if (n == "max_sweeps") ctx->opt_max_sweeps = std::max(1, (int)value);
+    else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
+    else return fail(ctx, "unknown option " + n);
+    ctx->plan_valid = false;
+    return 0;
+}
+
+int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *const *obs, const int32_t *lengths,
+                           int npop, const int32_t *keys, int n_keys)
+{
+    if (!ctx) return 1;
+    if (n_contigs <= 0 || !obs || !lengths) return fail(ctx, "set_contigs: no contigs");
+    if (npop < 1 || npop > 2) return fail(ctx, "set_contigs: npop must be 1 or 2");
+    CU(cudaSetDevice(ctx->device));
+    const int W = 1 + 3 * npop, Q = 3 * npop;
+    ctx->C = n_contigs;
+    ctx->npop = npop;
+    ctx->blk_off.assign(n_contigs + 1, 0);
+    for (int c = 0; c < n_contigs; ++c) {
+        if (lengths[c] <= 0) return fail(ctx, "set_contigs: empty contig");
+        ctx->blk_off[c + 1] = ctx->blk_off[c] + lengths[c];
+    }
+    ctx->total = ctx->blk_off[n_contigs];
+    // pass 1: validate spans, collect the key universe and which keys occur with span > 1
+    std::unordered_map<KeyRow, int, KeyRowHash> seen;  // value: bit0 = seen, bit1 = seen with span > 1
+    for (int c = 0; c < n_contigs; ++c) {
+        const int32_t *o = obs[c];
+        KeyRow last{};
+        int *last_flags = nullptr;
+        for (int64_t l = 0; l < lengths[c]; ++l) {
+            const int32_t *row = o + l * W;
+            if (row[0] <= 0) return fail(ctx, "data are malformed: span <= 0");  // reference src/inference_manager.cpp:243-244
+            KeyRow kr{};
+            for (int q = 0; q < Q; ++q) kr.v[q] = row[1 + q];
+            if (!last_flags || !(kr == last)) {
+                last_flags = &seen[kr];
+                last = kr;
+            }
+            *last_flags |= 1 | (row[0] > 1 ? 2 : 0);
+        }
+    }
+    // key table: explicit (global) or derived; order = lexicographic (reference include/block_key.h:51-60)
+    std::vector<KeyRow> table;
+    if (keys && n_keys > 0) {
+        for (int k = 0; k < n_keys; ++k) {
+            KeyRow kr{};
+            for (int q = 0; q < Q; ++q) kr.v[q] = keys[(size_t)k * Q + q];
+            table.push_back(kr);
+        }
+        for (size_t k = 1; k < table.size(); ++k)
+            if (!std::lexicographical_compare(table[k - 1].v.begin(), table[k - 1].v.begin() + Q, table[k].v.begin(),
+                                              table[k].v.begin() + Q))
+                return fail(ctx, "set_contigs: explicit key table is not strictly sorted");
+    } else {
+        for (const auto &kv : seen) table.push_back(kv.first);
+        std::sort(table.begin(), table.end(), [Q](const KeyRow &a, const KeyRow &b) {
+            return std::lexicographical_compare(a.v.begin(), a.v.begin() + Q, b.v.begin(), b.v.begin() + Q);
+        });
+    }
+    if (table.size() >= 65535) return fail(ctx, "set_contigs: more than 65534 distinct observation keys");
+    const int K = (int)table.size();
+    ctx->K = K;
+    ctx->keys.assign((size_t)K * Q, 0);
+    std::unordered_map<KeyRow, int, KeyRowHash> index;
+    for (int k = 0; k < K; ++k) {
+        for (int q = 0; q < Q; ++q) ctx->keys[(size_t)k * Q + q] = table[k].v[q];
+        index[table[k]] = k;
+    }
+    ctx->eig_of_key.assign(K, -1);
+    ctx->eig_keys.clear();
+    {
+        std::vector<int> eig;
+        for (const auto &kv : seen) {
+            auto it = index.find(kv.first);
+            if (it == index.end()) return fail(ctx, "set_contigs: observation key missing from the explicit key table");
+            if (kv.second & 2) eig.push_back(it->second);
+        }
+        std::sort(eig.begin(), eig.end());
+        for (int k : eig) {
+            ctx->eig_of_key[k] = (int)ctx->eig_keys.size();
+            ctx->eig_keys.push_back(k);
+        }
+    }
+    ctx->n_eig = (int)ctx->eig_keys.size();
+    if (ctx->n_eig > kMaxEig) return fail(ctx, "set_contigs: more than 30 distinct keys occur with span > 1");
+    // pass 2: per-block span / key id, per-contig presence
+    ctx->h_span.resize(ctx->total);
+    ctx->h_key.resize(ctx->total);
+    ctx->present.assign((size_t)n_contigs * K, 0);
+    for (int c = 0; c < n_contigs; ++c) {
+        const int32_t *o = obs[c];
+        KeyRow last{};
+        int last_id = -1;
+        const int64_t g0 = ctx->blk_off[c];
+        for (int64_t l = 0; l < lengths[c]; ++l) {
+            const int32_t *row = o + l * W;
+            KeyRow kr{};
+            for (int q = 0; q < Q; ++q) kr.v[q] = row[1 + q];
+            if (last_id < 0 || !(kr == last)) {
+                last_id = index[kr];
+                last = kr;
+            }
+            ctx->h_span[g0 + l] = row[0];
+            ctx->h_key[g0 + l] = (uint16_t)last_id;
+            ctx->present[(size_t)c * K + last_id] = 1;
+        }
+    }
+    CU(ctx->d_span.ensure(ctx->total));
+    CU(ctx->d_key.ensure(ctx->total));
+    CU(cudaMemcpy(ctx->d_span.p, ctx->h_span.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_key.p, ctx->h_key.data(), ctx->total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(ctx->d_blk_off.ensure(n_contigs + 1));
+    CU(cudaMemcpy(ctx->d_blk_off.p, ctx->blk_off.data(), (n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CU(ctx->d_eig_of_key.ensure(K));
+    CU(cudaMemcpy(ctx->d_eig_of_key.p, ctx->eig_of_key.data(), K * sizeof(int), cudaMemcpyHostToDevice));
+    CU(ctx->d_key_of_eig.ensure(std::max(1, ctx->n_eig)));
+    if (ctx->n_eig)
+        CU(cudaMemcpy(ctx->d_key_of_eig.p, ctx->eig_keys.data(), ctx->n_eig * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->plan_valid = false;
+    ctx->M = 0;
+    return 0;
+}
+
+int smcpp_b200_num_keys(const smcpp_b200_ctx *ctx) { return ctx ? ctx->K : -1; }
+int smcpp_b200_get_keys(const smcpp_b200_ctx *ctx, int32_t *keys)
+{
+    if (!ctx || !keys) return 1;
+    std::memcpy(keys, ctx->keys.data(), ctx->keys.size() * sizeof(int32_t));
+    return 0;
+}
+int smcpp_b200_num_eig_keys(const smcpp_b200_ctx *ctx) { return ctx ? ctx->n_eig : -1; }
+int smcpp_b200_get_eig_keys(const smcpp_b200_ctx *ctx, int32_t *key_idx)
+{
+    if (!ctx || !key_idx) return 1;
+    std::memcpy(key_idx, ctx->eig_keys.data(), ctx->eig_keys.size() * sizeof(int32_t));
+    return 0;
+}
+int smcpp_b200_get_key_present(const smcpp_b200_ctx *ctx, uint8_t *present)
+{
+    if (!ctx || !present) return 1;
+    std::memcpy(present, ctx->present.data(), ctx->present.size());
+    return 0;
+}
+int64_t smcpp_b200_total_blocks(const smcpp_b200_ctx *ctx) { return ctx ? ctx->total : -1; }
+
+}  // extern "C"
+
+// ---- chunk / slab plan and buffer allocation --------------------------------------------------------
+static int make_plan(smcpp_b200_ctx *ctx, int M)
+{
+    const int Mp = ((M + 31) / 32) * 32;
+    int burn = ctx->opt_burn_in + ctx->burn_in_adapt;
+    if (burn < 0) burn = 0;
+    int64_t maxL = 0;
+    for (int c = 0; c < ctx->C; ++c) maxL = std::max<int64_t>(maxL, ctx->blk_off[c + 1] - ctx->blk_off[c]);
+    int Lc;
+    if (ctx->opt_force_sequential) Lc = (int)maxL;
+    else if (ctx->opt_chunk_blocks > 0) Lc = ctx->opt_chunk_blocks;
+    else {
+        int64_t per = (ctx->total + ctx->opt_target_warps - 1) / ctx->opt_target_warps;
+        Lc = (int)std::max<int64_t>(per, std::max(burn, 64));
+    }
+    if (Lc > maxL) Lc = (int)maxL;
+    if (Lc < 1) Lc = 1;
+    const int slab = ctx->opt_slab_blocks;
+    const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M;
+    ctx->plan_burn = burn;
+    if (same) return 0;
+    CU(cudaSetDevice(ctx->device));
+    const int C = ctx->C;
+    ctx->chunk_off.assign(C + 1, 0);
+    ctx->slab_off.assign(C + 1, 0);
+    ctx->col_off.assign(C, 0);
+    std::vector<int32_t> ch_contig, ch_start, ch_len, sl_contig, sl_start, sl_len;
+    std::vector<uint32_t> sl_mask;
+    int64_t cols = 0;
+    for (int c = 0; c < C; ++c) {
+        const int64_t L = ctx->blk_off[c + 1] - ctx->blk_off[c];
+        const int nch = (int)((L + Lc - 1) / Lc);
+        ctx->col_off[c] = cols;
+        cols += (int64_t)nch * (Lc + 1);
+        for (int i = 0; i < nch; ++i) {
+            ch_contig.push_back(c);
+            ch_start.push_back(i * Lc);
+            ch_len.push_back((int)std::min<int64_t>(Lc, L - (int64_t)i * Lc));
+        }
+        ctx->chunk_off[c + 1] = (int)ch_contig.size();
+        const int nsl = (int)((L + slab - 1) / slab);
+        for (int i = 0; i < nsl; ++i) {
+            const int s0 = i * slab, n = (int)std::min<int64_t>(slab, L - (int64_t)i * slab);
+            uint32_t mask = 0;
+            const int64_t g0 = ctx->blk_off[c] + s0;
+            for (int b = 0; b < n; ++b) {
+                if (ctx->h_span[g0 + b] == 1) mask |= 1u;
+                else mask |= 2u << ctx->eig_of_key[ctx->h_key[g0 + b]];
+            }
+            sl_contig.push_back(c);
+            sl_start.push_back(s0);
+            sl_len.push_back(n);
+            sl_mask.push_back(mask);
+        }
+        ctx->slab_off[c + 1] = (int)sl_contig.size();
+    }
+    ctx->n_chunks = (int)ch_contig.size();
+    ctx->n_slabs = (int)sl_contig.size();
+    ctx->n_cols = cols;
+    ctx->plan_Lc = Lc;
+    ctx->plan_slab = slab;
+    ctx->M = M;
+    ctx->Mp = Mp;
+#define UP(buf, vec)                                                                                             \
+    CU(ctx->buf.ensure((vec).size()));                                                                           \
+    CU(cudaMemcpy(ctx->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+    UP(d_chunk_off, ctx->chunk_off);
+    UP(d_slab_off, ctx->slab_off);
+    UP(d_col_off, ctx->col_off);
+    UP(d_ch_contig, ch_contig);
+    UP(d_ch_start, ch_start);
+    UP(d_ch_len, ch_len);
+    UP(d_sl_contig, sl_contig);
+    UP(d_sl_start, sl_start);
+    UP(d_sl_len, sl_len);
+    UP(d_sl_mask, sl_mask);
+#undef UP
+    const int K = ctx->K, NE = std::max(1, ctx->n_eig);
+    const size_t MM = (size_t)Mp * Mp;
+    CU(ctx->m_pi.ensure(Mp));
+    CU(ctx->m_Td.ensure((size_t)M * Mp));
+    CU(ctx->m_TdT.ensure((size_t)M * Mp));
+    CU(ctx->m_E.ensure((size_t)K * Mp));
+    CU(ctx->m_A32.ensure((size_t)K * M * Mp));
+    CU(ctx->m_P.ensure((size_t)NE * M * Mp));
+    CU(ctx->m_PT.ensure((size_t)NE * M * Mp));
+    CU(ctx->m_Pinv.ensure((size_t)NE * M * Mp));
+    CU(ctx->m_PinvT.ensure((size_t)NE * M * Mp));
+    CU(ctx->m_dsc.ensure((size_t)NE * Mp));
+    CU(ctx->m_logd.ensure((size_t)NE * Mp));
+    CU(ctx->m_dr.ensure((size_t)NE * Mp));
+    CU(ctx->m_scale.ensure(NE));
+    CU(ctx->m_logscale.ensure(NE));
+    CU(ctx->w_alpha.ensure((size_t)cols * Mp));
+    CU(ctx->w_cnorm.ensure(ctx->total));
+    CU(ctx->w_bvec.ensure((size_t)ctx->total * Mp));
+    CU(ctx->w_start_used.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_end_alpha.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_end_alpha_prev.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_ll_chunk.ensure(ctx->n_chunks));
+    CU(ctx->w_bstart_used.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_beta_out.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_beta_out_prev.ensure((size_t)ctx->n_chunks * Mp));
+    CU(ctx->w_fwd_flag.ensure(ctx->n_chunks));
+    CU(ctx->w_bwd_flag.ensure(ctx->n_chunks));
+    CU(ctx->w_counters.ensure(8));
+    CU(ctx->h_counters.ensure(8));
+    CU(ctx->w_Xpart.ensure((size_t)ctx->n_slabs * MM));
+    CU(ctx->w_Rpart.ensure((size_t)ctx->n_slabs * NE * MM));
+    CU(ctx->w_dpart.ensure((size_t)ctx->n_slabs * NE * Mp));
+    CU(ctx->w_gspart.ensure((size_t)ctx->n_slabs * K * Mp));
+    CU(ctx->w_scratch.ensure((size_t)C * 3 * MM));
+    CU(ctx->o_ll.ensure(C));
+    CU(ctx->o_xisum.ensure((size_t)C * M * M));
+    CU(ctx->o_gamma0.ensure((size_t)C * M));
+    CU(ctx->o_gamma_sums.ensure((size_t)C * K * M));
+    const size_t nred = 1 + M + (size_t)M * M + (size_t)K * M;
+    CU(ctx->o_reduced.ensure(nred));
+    CU(ctx->h_out.ensure((size_t)C * (1 + M + (size_t)M * M + (size_t)K * M) + nred));
+    const size_t nin = (size_t)M + (size_t)M * M + (size_t)K * M + (size_t)NE * (2 * (size_t)M * M + 2 * M + 1);
+    CU(ctx->d_in.ensure(nin));
+    CU(ctx->h_in.ensure(nin));
+    ctx->plan_valid = true;
+    return 0;
+}
+
+static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_eig,
+                     const double *P, const double *Pinv, const double *d, const double *dsc, const double *scale,
+                     bool upload)
+{
+    if (ctx->C == 0) return fail(ctx, "estep: set_contigs() has not been called");
+    if (M < 1 || M > kMaxMp) return fail(ctx, "estep: M must be in [1, 128]");
+    CU(cudaSetDevice(ctx->device));
+    if (make_plan(ctx, M)) return 1;
+    const int K = ctx->K, NE = ctx->n_eig;
+    if (upload) {
+        if (!pi || !T || !E) return fail(ctx, "estep: pi, T and E are required");
+        if (!P) {
+            // library-side eigensystems (host QR algorithm), same routine as smcpp_b200_eigensystems()
+            ctx->eig_store.resize((size_t)NE * (2 * (size_t)M * M + 2 * M + 1));
+            double *eP = ctx->eig_store.data(), *ePi = eP + (size_t)NE * M * M, *ed = ePi + (size_t)NE * M * M,
+                   *eds = ed + (size_t)NE * M, *esc = eds + (size_t)NE * M;
+            std::vector<int32_t> cplx(std::max(1, NE));
+            std::string msg;
+            if (smcb::host_eigensystems(M, K, NE, ctx->eig_keys.data(), T, E, eP, ePi, ed, eds, esc, cplx.data(), &msg))
+                return fail(ctx, "estep: eigensystems: " + msg);
+            P = eP; Pinv = ePi; d = ed; dsc = eds; scale = esc;
+        } else if (n_eig != NE) {
+            return fail(ctx, "estep: n_eig does not match the number of keys that occur with span > 1");
+        }
+        double *h = ctx->h_in.p;
+        size_t o = 0;
+        auto put = [&](const double *src, size_t n) { if (n) std::memcpy(h + o, src, n * sizeof(double)); o += n; };
+        const size_t o_pi = 0; put(pi, M);
+        const size_t o_T = o; put(T, (size_t)M * M);
+        const size_t o_E = o; put(E, (size_t)K * M);
+        const size_t o_P = o; put(P, (size_t)NE * M * M);
+        const size_t o_Pi = o; put(Pinv, (size_t)NE * M * M);
+        const size_t o_d = o; put(d, (size_t)NE * M);
+        const size_t o_ds = o; put(dsc, (size_t)NE * M);
+        const size_t o_sc = o; put(scale, NE);
+        cudaEventRecord(ctx->ev[0], ctx->st);
+        CU(cudaMemcpyAsync(ctx->d_in.p, h, o * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        const double *di = ctx->d_in.p;
+        launch_setup(ctx->model(), di + o_pi, di + o_T, di + o_E, di + o_P, di + o_Pi, di + o_d, di + o_ds, di + o_sc, ctx->st);
+        ctx->stats.kernel_launches = 1;
+    } else {
+        cudaEventRecord(ctx->ev[0], ctx->st);
+        ctx->stats.kernel_launches = 0;
+    }
+    const Model m = ctx->model();
+    const Plan p = ctx->plan();
+    const Work w = ctx->work();
+    cudaEventRecord(ctx->ev[1], ctx->st);
+    CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
+    cudaEventRecord(ctx->ev_setup_done, ctx->st);
+    // backward recursion runs concurrently on the second stream (it does not depend on alpha)
+    CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
+    launch_backward(m, p, w, 0, ctx->st2);
+    launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st2);
+    // forward recursion
+    launch_forward(m, p, w, 0, ctx->st);
+    launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
+    ctx->stats.kernel_launches += 4;
+    cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0));
+    int fwd_sweeps = 1, bwd_sweeps = 1, fwd_redone = 0, bwd_redone = 0;
+    float fwd_mm = 0.f, bwd_mm = 0.f;
+    for (;;) {
+        CU(cudaMemcpyAsync(ctx->h_counters.p, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        const int nf = ctx->h_counters.p[0], nb = ctx->h_counters.p[1];
+        float f;
+        std::memcpy(&f, &ctx->h_counters.p[2], 4); fwd_mm = std::max(fwd_mm, f);
+        std::memcpy(&f, &ctx->h_counters.p[3], 4); bwd_mm = std::max(bwd_mm, f);
+        if (nf == 0 && nb == 0) break;
+        if (fwd_sweeps + bwd_sweeps > ctx->opt_max_sweeps) break;
+        CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
+        if (nf) {
+            CU(cudaMemcpyAsync(w.end_alpha_prev, w.end_alpha, (size_t)p.n_chunks * m.Mp * sizeof(float),
+                               cudaMemcpyDeviceToDevice, ctx->st));
+            launch_forward(m, p, w, fwd_sweeps, ctx->st);
+            launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
+            ++fwd_sweeps;
+            fwd_redone += nf;
+            ctx->stats.kernel_launches += 2;
+        }
+        if (nb) {
+            CU(cudaMemcpyAsync(w.beta_out_prev, w.beta_out, (size_t)p.n_chunks * m.Mp * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->st));
+            launch_backward(m, p, w, bwd_sweeps, ctx->st);
+            launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st);
+            ++bwd_sweeps;
+            bwd_redone += nb;
+            ctx->stats.kernel_launches += 2;
+        }
+    }
+    // a failed boundary check means the burn-in was too short for this model: lengthen it for the next E-step
+    if ((fwd_redone || bwd_redone) && !ctx->opt_force_sequential) {
+        const int cur = ctx->opt_burn_in + ctx->burn_in_adapt;
+        ctx->burn_in_adapt += std::max(cur, 256);
+    }
+    cudaEventRecord(ctx->ev[2], ctx->st);
+    launch_stats(m, p, w, ctx->st);
+    cudaEventRecord(ctx->ev[3], ctx->st);
+    launch_finalize(m, p, w, ctx->st);
+    cudaEventRecord(ctx->ev[4], ctx->st);
+    ctx->stats.kernel_launches += 3;
+    CU(cudaGetLastError());
+    ctx->stats.n_chunks = p.n_chunks;
+    ctx->stats.chunk_blocks = p.chunk_blocks;
+    ctx->stats.burn_in_blocks = p.burn_in;
+    ctx->stats.fwd_sweeps = fwd_sweeps;
+    ctx->stats.bwd_sweeps = bwd_sweeps;
+    ctx->stats.fwd_redone = fwd_redone;
+    ctx->stats.bwd_redone = bwd_redone;
+    ctx->stats.fwd_max_mismatch = fwd_mm;
+    ctx->stats.bwd_max_mismatch = bwd_mm;
+    return 0;
+}
+
+static int finish_timing(smcpp_b200_ctx *ctx)
+{
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.ms_setup = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_forward = ms;  // forward || backward + sweeps
+    ctx->stats.ms_backward = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_stats = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_finalize = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stats.ms_total = ms;
+    return 0;
+}
+
+extern "C" {
+
+int smcpp_b200_eigensystems(smcpp_b200_ctx *ctx, int M, const double *T, const double *E, double *P, double *Pinv,
+                            double *d, double *d_scaled, double *scale, int32_t *cplx)
+{
+    if (!ctx) return 1;
+    std::string msg;
+    if (smcb::host_eigensystems(M, ctx->K, ctx->n_eig, ctx->eig_keys.data(), T, E, P, Pinv, d, d_scaled, scale, cplx, &msg))
+        return fail(ctx, "eigensystems: " + msg);
+    return 0;
+}
+
+int smcpp_b200_host_eig(int n, const double *A, double *P, double *Pinv, double *d_re, double *d_im)
+{
+    if (n < 1 || !A || !P || !Pinv || !d_re || !d_im) return 1;
+    return smcb::host_eig_real_general(n, A, P, Pinv, d_re, d_im, nullptr);
+}
+
+int smcpp_b200_host_eigensystems(int M, int K, int n_eig, const int32_t *eig_key_idx, const double *T, const double *E,
+                                 double *P, double *Pinv, double *d, double *d_scaled, double *scale, int32_t *cplx)
+{
+    if (M < 1 || K < 1 || n_eig < 0 || (n_eig && !eig_key_idx) || !T || !E) return 1;
+    return smcb::host_eigensystems(M, K, n_eig, eig_key_idx, T, E, P, Pinv, d, d_scaled, scale, cplx, nullptr);
+}
+
+int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)
+{
+    if (!ctx || !ctx->plan_valid) return 1;
+    CU(cudaSetDevice(ctx->device));
+    const int C = ctx->C, M = ctx->M, K = ctx->K;
+    double *h = ctx->h_out.p;
+    size_t o = 0;
+    const size_t n_ll = C, n_x = (size_t)C * M * M, n_g0 = (size_t)C * M, n_gs = (size_t)C * K * M,
+                 n_r = 1 + M + (size_t)M * M + (size_t)K * M;
+    double *h_ll = h + o; o += n_ll;
+    double *h_x = h + o; o += n_x;
+    double *h_g0 = h + o; o += n_g0;
+    double *h_gs = h + o; o += n_gs;
+    double *h_r = h + o;
+    if (ll) CU(cudaMemcpyAsync(h_ll, ctx->o_ll.p, n_ll * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (xisum) CU(cudaMemcpyAsync(h_x, ctx->o_xisum.p, n_x * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (gamma0) CU(cudaMemcpyAsync(h_g0, ctx->o_gamma0.p, n_g0 * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (gamma_sums) CU(cudaMemcpyAsync(h_gs, ctx->o_gamma_sums.p, n_gs * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (reduced) CU(cudaMemcpyAsync(h_r, ctx->o_reduced.p, n_r * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ll) std::memcpy(ll, h_ll, n_ll * 8);
+    if (xisum) std::memcpy(xisum, h_x, n_x * 8);
+    if (gamma0) std::memcpy(gamma0, h_g0, n_g0 * 8);
+    if (gamma_sums) std::memcpy(gamma_sums, h_gs, n_gs * 8);
+    if (reduced) std::memcpy(reduced, h_r, n_r * 8);
+    return 0;
+}
+
+int smcpp_b200_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_eig,
+                     const double *P, const double *Pinv, const double *d, const double *d_scaled, const double *scale,
+                     double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)
+{
+    if (!ctx) return 1;
+    if (run_estep(ctx, M, pi, T, E, n_eig, P, Pinv, d, d_scaled, scale, true)) return 1;
+    if (smcpp_b200_fetch(ctx, ll, xisum, gamma0, gamma_sums, reduced)) return 1;
+    return finish_timing(ctx);
+}
+
+int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_eig,
+                            const double *P, const double *Pinv, const double *d, const double *d_scaled,
+                            const double *scale, int upload_inputs)
+{
+    if (!ctx) return 1;
+    if (!upload_inputs && (!ctx->plan_valid || ctx->M != M)) return fail(ctx, "estep_device: no resident inputs for this M");
+    if (run_estep(ctx, M, pi, T, E, n_eig, P, Pinv, d, d_scaled, scale, upload_inputs != 0)) return 1;
+    return finish_timing(ctx);
+}
+
+int smcpp_b200_reduced_device_ptr(smcpp_b200_ctx *ctx, void **ptr, int64_t *count)
+{
+    if (!ctx || !ctx->plan_valid || !ptr || !count) return 1;
+    *ptr = ctx->o_reduced.p;
+    *count = 1 + ctx->M + (int64_t)ctx->M * ctx->M + (int64_t)ctx->K * ctx->M;
+    return 0;
+}
+
+int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out)
+{
+    if (!ctx || !out) return 1;
+    *out = ctx->stats;
+    return 0;
+}
+
+int smcpp_b200_stream(smcpp_b200_ctx *ctx, void **stream)
+{
+    if (!ctx || !stream) return 1;
+    *stream = (void *)ctx->st;
+    return 0;
+}
+
+int smcpp_b200_debug_alpha_hat(smcpp_b200_ctx *ctx, int contig, float *out)
+{
+    if (!ctx || !ctx->plan_valid || contig < 0 || contig >= ctx->C || !out) return 1;
+    CU(cudaSetDevice(ctx->device));
+    const int64_t L = ctx->blk_off[contig + 1] - ctx->blk_off[contig];
+    const size_t n = (size_t)(L + 1) * ctx->M;
+    float *dbuf = nullptr;
+    CU(cudaMalloc(&dbuf, n * sizeof(float)));
+    launch_gather_alpha(ctx->model(), ctx->plan(), ctx->work(), contig, dbuf, ctx->st);
+    cudaError_t e = cudaMemcpyAsync(out, dbuf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+    cudaFree(dbuf);
+    if (e != cudaSuccess) return fail(ctx, std::string("debug_alpha_hat: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

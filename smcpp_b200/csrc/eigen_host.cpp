@@ -1,0 +1,474 @@
+// smcpp_b200 -- real non-symmetric eigensolver on the host (Householder reduction to Hessenberg form,
+// Francis double-shift QR with accumulation, back-substitution): the classical EISPACK orthes/ortran/hqr2
+// sequence, which is also what the reference's Eigen::EigenSolver descends from.  Results are compared
+// through P diag(d) Pinv (tests/test_eigen.py), never eigenvector by eigenvector.
+#include "eigen_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+namespace smcb {
+namespace {
+
+struct Mat {
+    int n;
+    std::vector<double> a;
+    explicit Mat(int n_) : n(n_), a((size_t)n_ * n_, 0.0) {}
+    double &operator()(int i, int j) { return a[(size_t)i * n + j]; }
+    double operator()(int i, int j) const { return a[(size_t)i * n + j]; }
+};
+
+void hessenberg(Mat &H, Mat &V)
+{
+    const int n = H.n, low = 0, high = n - 1;
+    std::vector<double> ort(n, 0.0);
+    for (int m = low + 1; m <= high - 1; ++m) {
+        double scale = 0.0;
+        for (int i = m; i <= high; ++i) scale += std::fabs(H(i, m - 1));
+        if (scale == 0.0) continue;
+        double h = 0.0;
+        for (int i = high; i >= m; --i) {
+            ort[i] = H(i, m - 1) / scale;
+            h += ort[i] * ort[i];
+        }
+        double g = std::sqrt(h);
+        if (ort[m] > 0) g = -g;
+        h -= ort[m] * g;
+        ort[m] -= g;
+        for (int j = m; j < n; ++j) {
+            double f = 0.0;
+            for (int i = high; i >= m; --i) f += ort[i] * H(i, j);
+            f /= h;
+            for (int i = m; i <= high; ++i) H(i, j) -= f * ort[i];
+        }
+        for (int i = 0; i <= high; ++i) {
+            double f = 0.0;
+            for (int j = high; j >= m; --j) f += ort[j] * H(i, j);
+            f /= h;
+            for (int j = m; j <= high; ++j) H(i, j) -= f * ort[j];
+        }
+        ort[m] *= scale;
+        H(m, m - 1) = scale * g;
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) V(i, j) = i == j ? 1.0 : 0.0;
+    for (int m = high - 1; m >= low + 1; --m) {
+        if (H(m, m - 1) == 0.0) continue;
+        for (int i = m + 1; i <= high; ++i) ort[i] = H(i, m - 1);
+        for (int j = m; j <= high; ++j) {
+            double g = 0.0;
+            for (int i = m; i <= high; ++i) g += ort[i] * V(i, j);
+            g = (g / ort[m]) / H(m, m - 1);
+            for (int i = m; i <= high; ++i) V(i, j) += g * ort[i];
+        }
+    }
+}
+
+inline void cdiv(double xr, double xi, double yr, double yi, double &zr, double &zi)
+{
+    double r, d;
+    if (std::fabs(yr) > std::fabs(yi)) {
+        r = yi / yr;
+        d = yr + r * yi;
+        zr = (xr + r * xi) / d;
+        zi = (xi - r * xr) / d;
+    } else {
+        r = yr / yi;
+        d = yi + r * yr;
+        zr = (r * xr + xi) / d;
+        zi = (r * xi - xr) / d;
+    }
+}
+
+// H upper Hessenberg (destroyed: becomes quasi-triangular T, then holds the triangular eigenvectors),
+// V accumulates; on return the columns of V are the (real / real+imag pair) eigenvectors.
+int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e)
+{
+    const int nn = H.n, low = 0, high = nn - 1;
+    int n = nn - 1;
+    const double eps = std::ldexp(1.0, -52);
+    double exshift = 0.0, p = 0, q = 0, r = 0, s = 0, z = 0, t, w, x, y;
+    double norm = 0.0;
+    for (int i = 0; i < nn; ++i)
+        for (int j = std::max(i - 1, 0); j < nn; ++j) norm += std::fabs(H(i, j));
+    int iter = 0, total_iter = 0;
+    while (n >= low) {
+        int l = n;
+        while (l > low) {
+            s = std::fabs(H(l - 1, l - 1)) + std::fabs(H(l, l));
+            if (s == 0.0) s = norm;
+            if (std::fabs(H(l, l - 1)) < eps * s) break;
+            --l;
+        }
+        if (l == n) {
+            H(n, n) += exshift;
+            d[n] = H(n, n);
+            e[n] = 0.0;
+            --n;
+            iter = 0;
+        } else if (l == n - 1) {
+            w = H(n, n - 1) * H(n - 1, n);
+            p = (H(n - 1, n - 1) - H(n, n)) / 2.0;
+            q = p * p + w;
+            z = std::sqrt(std::fabs(q));
+            H(n, n) += exshift;
+            H(n - 1, n - 1) += exshift;
+            x = H(n, n);
+            if (q >= 0) {
+                z = p >= 0 ? p + z : p - z;
+                d[n - 1] = x + z;
+                d[n] = d[n - 1];
+                if (z != 0.0) d[n] = x - w / z;
+                e[n - 1] = 0.0;
+                e[n] = 0.0;
+                x = H(n, n - 1);
+                s = std::fabs(x) + std::fabs(z);
+                p = x / s;
+                q = z / s;
+                r = std::sqrt(p * p + q * q);
+                p /= r;
+                q /= r;
+                for (int j = n - 1; j < nn; ++j) {
+                    z = H(n - 1, j);
+                    H(n - 1, j) = q * z + p * H(n, j);
+                    H(n, j) = q * H(n, j) - p * z;
+                }
+                for (int i = 0; i <= n; ++i) {
+                    z = H(i, n - 1);
+                    H(i, n - 1) = q * z + p * H(i, n);
+                    H(i, n) = q * H(i, n) - p * z;
+                }
+                for (int i = low; i <= high; ++i) {
+                    z = V(i, n - 1);
+                    V(i, n - 1) = q * z + p * V(i, n);
+                    V(i, n) = q * V(i, n) - p * z;
+                }
+            } else {
+                d[n - 1] = x + p;
+                d[n] = x + p;
+                e[n - 1] = z;
+                e[n] = -z;
+            }
+            n -= 2;
+            iter = 0;
+        } else {
+            x = H(n, n);
+            y = 0.0;
+            w = 0.0;
+            if (l < n) {
+                y = H(n - 1, n - 1);
+                w = H(n, n - 1) * H(n - 1, n);
+            }
+            if (iter == 10) {  // Wilkinson's exceptional shift
+                exshift += x;
+                for (int i = low; i <= n; ++i) H(i, i) -= x;
+                s = std::fabs(H(n, n - 1)) + std::fabs(H(n - 1, n - 2));
+                x = y = 0.75 * s;
+                w = -0.4375 * s * s;
+            }
+            if (iter == 30) {  // second exceptional shift
+                s = (y - x) / 2.0;
+                s = s * s + w;
+                if (s > 0) {
+                    s = std::sqrt(s);
+                    if (y < x) s = -s;
+                    s = x - w / ((y - x) / 2.0 + s);
+                    for (int i = low; i <= n; ++i) H(i, i) -= s;
+                    exshift += s;
+                    x = y = w = 0.964;
+                }
+            }
+            ++iter;
+            if (++total_iter > 60 * nn + 200) return 1;
+            int m = n - 2;
+            while (m >= l) {
+                z = H(m, m);
+                r = x - z;
+                s = y - z;
+                p = (r * s - w) / H(m + 1, m) + H(m, m + 1);
+                q = H(m + 1, m + 1) - z - r - s;
+                r = H(m + 2, m + 1);
+                s = std::fabs(p) + std::fabs(q) + std::fabs(r);
+                p /= s;
+                q /= s;
+                r /= s;
+                if (m == l) break;
+                if (std::fabs(H(m, m - 1)) * (std::fabs(q) + std::fabs(r)) <
+                    eps * (std::fabs(p) * (std::fabs(H(m - 1, m - 1)) + std::fabs(z) + std::fabs(H(m + 1, m + 1)))))
+                    break;
+                --m;
+            }
+            for (int i = m + 2; i <= n; ++i) {
+                H(i, i - 2) = 0.0;
+                if (i > m + 2) H(i, i - 3) = 0.0;
+            }
+            for (int k = m; k <= n - 1; ++k) {
+                const bool notlast = k != n - 1;
+                if (k != m) {
+                    p = H(k, k - 1);
+                    q = H(k + 1, k - 1);
+                    r = notlast ? H(k + 2, k - 1) : 0.0;
+                    x = std::fabs(p) + std::fabs(q) + std::fabs(r);
+                    if (x == 0.0) continue;
+                    p /= x;
+                    q /= x;
+                    r /= x;
+                }
+                s = std::sqrt(p * p + q * q + r * r);
+                if (p < 0) s = -s;
+                if (s != 0) {
+                    if (k != m) H(k, k - 1) = -s * x;
+                    else if (l != m) H(k, k - 1) = -H(k, k - 1);
+                    p += s;
+                    x = p / s;
+                    y = q / s;
+                    z = r / s;
+                    q /= p;
+                    r /= p;
+                    for (int j = k; j < nn; ++j) {
+                        p = H(k, j) + q * H(k + 1, j);
+                        if (notlast) {
+                            p += r * H(k + 2, j);
+                            H(k + 2, j) -= p * z;
+                        }
+                        H(k, j) -= p * x;
+                        H(k + 1, j) -= p * y;
+                    }
+                    for (int i = 0; i <= std::min(n, k + 3); ++i) {
+                        p = x * H(i, k) + y * H(i, k + 1);
+                        if (notlast) {
+                            p += z * H(i, k + 2);
+                            H(i, k + 2) -= p * r;
+                        }
+                        H(i, k) -= p;
+                        H(i, k + 1) -= p * q;
+                    }
+                    for (int i = low; i <= high; ++i) {
+                        p = x * V(i, k) + y * V(i, k + 1);
+                        if (notlast) {
+                            p += z * V(i, k + 2);
+                            V(i, k + 2) -= p * r;
+                        }
+                        V(i, k) -= p;
+                        V(i, k + 1) -= p * q;
+                    }
+                }
+            }
+        }
+    }
+    if (norm == 0.0) return 0;
+    // back-substitution: eigenvectors of the quasi-triangular matrix
+    for (n = nn - 1; n >= 0; --n) {
+        p = d[n];
+        q = e[n];
+        if (q == 0) {
+            int l = n;
+            H(n, n) = 1.0;
+            for (int i = n - 1; i >= 0; --i) {
+                w = H(i, i) - p;
+                r = 0.0;
+                for (int j = l; j <= n; ++j) r += H(i, j) * H(j, n);
+                if (e[i] < 0.0) {
+                    z = w;
+                    s = r;
+                } else {
+                    l = i;
+                    if (e[i] == 0.0) {
+                        H(i, n) = w != 0.0 ? -r / w : -r / (eps * norm);
+                    } else {
+                        x = H(i, i + 1);
+                        y = H(i + 1, i);
+                        q = (d[i] - p) * (d[i] - p) + e[i] * e[i];
+                        t = (x * s - z * r) / q;
+                        H(i, n) = t;
+                        H(i + 1, n) = std::fabs(x) > std::fabs(z) ? (-r - w * t) / x : (-s - y * t) / z;
+                    }
+                    t = std::fabs(H(i, n));
+                    if ((eps * t) * t > 1)
+                        for (int j = i; j <= n; ++j) H(j, n) /= t;
+                }
+            }
+        } else if (q < 0) {
+            int l = n - 1;
+            if (std::fabs(H(n, n - 1)) > std::fabs(H(n - 1, n))) {
+                H(n - 1, n - 1) = q / H(n, n - 1);
+                H(n - 1, n) = -(H(n, n) - p) / H(n, n - 1);
+            } else {
+                cdiv(0.0, -H(n - 1, n), H(n - 1, n - 1) - p, q, H(n - 1, n - 1), H(n - 1, n));
+            }
+            H(n, n - 1) = 0.0;
+            H(n, n) = 1.0;
+            for (int i = n - 2; i >= 0; --i) {
+                double ra = 0.0, sa = 0.0, vr, vi;
+                for (int j = l; j <= n; ++j) {
+                    ra += H(i, j) * H(j, n - 1);
+                    sa += H(i, j) * H(j, n);
+                }
+                w = H(i, i) - p;
+                if (e[i] < 0.0) {
+                    z = w;
+                    r = ra;
+                    s = sa;
+                } else {
+                    l = i;
+                    if (e[i] == 0) {
+                        cdiv(-ra, -sa, w, q, H(i, n - 1), H(i, n));
+                    } else {
+                        x = H(i, i + 1);
+                        y = H(i + 1, i);
+                        vr = (d[i] - p) * (d[i] - p) + e[i] * e[i] - q * q;
+                        vi = (d[i] - p) * 2.0 * q;
+                        if (vr == 0.0 && vi == 0.0)
+                            vr = eps * norm * (std::fabs(w) + std::fabs(q) + std::fabs(x) + std::fabs(y) + std::fabs(z));
+                        cdiv(x * r - z * ra + q * sa, x * s - z * sa - q * ra, vr, vi, H(i, n - 1), H(i, n));
+                        if (std::fabs(x) > (std::fabs(z) + std::fabs(q))) {
+                            H(i + 1, n - 1) = (-ra - w * H(i, n - 1) + q * H(i, n)) / x;
+                            H(i + 1, n) = (-sa - w * H(i, n) - q * H(i, n - 1)) / x;
+                        } else {
+                            cdiv(-r - y * H(i, n - 1), -s - y * H(i, n), z, q, H(i + 1, n - 1), H(i + 1, n));
+                        }
+                    }
+                    t = std::max(std::fabs(H(i, n - 1)), std::fabs(H(i, n)));
+                    if ((eps * t) * t > 1)
+                        for (int j = i; j <= n; ++j) {
+                            H(j, n - 1) /= t;
+                            H(j, n) /= t;
+                        }
+                }
+            }
+        }
+    }
+    // back-transform with the accumulated orthogonal matrix
+    for (int j = nn - 1; j >= low; --j)
+        for (int i = low; i <= high; ++i) {
+            z = 0.0;
+            for (int k = low; k <= std::min(j, high); ++k) z += V(i, k) * H(k, j);
+            V(i, j) = z;
+        }
+    return 0;
+}
+
+// complex inverse by LU with partial pivoting (n <= 128)
+int complex_inverse(int n, std::vector<std::complex<double>> &A, std::vector<std::complex<double>> &Inv)
+{
+    typedef std::complex<double> cd;
+    std::vector<int> piv(n);
+    for (int i = 0; i < n; ++i) piv[i] = i;
+    for (int k = 0; k < n; ++k) {
+        int best = k;
+        double bv = std::abs(A[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            double v = std::abs(A[(size_t)i * n + k]);
+            if (v > bv) { bv = v; best = i; }
+        }
+        if (bv == 0.0) return 1;
+        if (best != k) {
+            for (int j = 0; j < n; ++j) std::swap(A[(size_t)k * n + j], A[(size_t)best * n + j]);
+            std::swap(piv[k], piv[best]);
+        }
+        const cd pivv = A[(size_t)k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const cd f = A[(size_t)i * n + k] / pivv;
+            A[(size_t)i * n + k] = f;
+            if (f != cd(0.0))
+                for (int j = k + 1; j < n; ++j) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+        }
+    }
+    Inv.assign((size_t)n * n, cd(0.0));
+    std::vector<cd> col(n);
+    for (int c = 0; c < n; ++c) {
+        for (int i = 0; i < n; ++i) col[i] = piv[i] == c ? cd(1.0) : cd(0.0);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < i; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
+        for (int i = n - 1; i >= 0; --i) {
+            for (int j = i + 1; j < n; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
+            col[i] /= A[(size_t)i * n + i];
+        }
+        for (int i = 0; i < n; ++i) Inv[(size_t)i * n + c] = col[i];
+    }
+    return 0;
+}
+
+}  // namespace
+
+int host_eig_real_general(int n, const double *A, double *P_r, double *Pinv_r, double *d_r, double *d_i, std::string *msg)
+{
+    typedef std::complex<double> cd;
+    Mat H(n), V(n);
+    std::copy(A, A + (size_t)n * n, H.a.begin());
+    std::vector<double> d(n, 0.0), e(n, 0.0);
+    if (n == 1) {
+        P_r[0] = 1.0; Pinv_r[0] = 1.0; d_r[0] = A[0]; d_i[0] = 0.0;
+        return 0;
+    }
+    hessenberg(H, V);
+    if (schur_vectors(H, V, d, e)) {
+        if (msg) *msg = "QR iteration did not converge";
+        return 1;
+    }
+    // complex eigenvector matrix, unit 2-norm columns (as Eigen's EigenSolver::eigenvectors())
+    std::vector<cd> Pc((size_t)n * n), Pinv;
+    for (int j = 0; j < n; ++j) {
+        if (e[j] == 0.0) {
+            double nrm = 0.0;
+            for (int i = 0; i < n; ++i) nrm += V(i, j) * V(i, j);
+            nrm = std::sqrt(nrm);
+            for (int i = 0; i < n; ++i) Pc[(size_t)i * n + j] = cd(V(i, j) / nrm, 0.0);
+        } else if (e[j] > 0.0 && j + 1 < n) {
+            double nrm = 0.0;
+            for (int i = 0; i < n; ++i) nrm += V(i, j) * V(i, j) + V(i, j + 1) * V(i, j + 1);
+            nrm = std::sqrt(nrm);
+            for (int i = 0; i < n; ++i) {
+                Pc[(size_t)i * n + j] = cd(V(i, j) / nrm, V(i, j + 1) / nrm);
+                Pc[(size_t)i * n + j + 1] = cd(V(i, j) / nrm, -V(i, j + 1) / nrm);
+            }
+            ++j;
+        }
+    }
+    std::vector<cd> LU = Pc;
+    if (complex_inverse(n, LU, Pinv)) {
+        if (msg) *msg = "eigenvector matrix is singular";
+        return 1;
+    }
+    for (size_t x = 0; x < (size_t)n * n; ++x) {
+        P_r[x] = Pc[x].real();
+        Pinv_r[x] = Pinv[x].real();
+    }
+    for (int i = 0; i < n; ++i) {
+        d_r[i] = d[i];
+        d_i[i] = e[i];
+    }
+    return 0;
+}
+
+int host_eigensystems(int M, int K, int n_eig, const int32_t *eig_keys, const double *T, const double *E, double *P,
+                      double *Pinv, double *d, double *d_scaled, double *scale, int32_t *cplx, std::string *msg)
+{
+    std::vector<double> A((size_t)M * M), di(M);
+    for (int e = 0; e < n_eig; ++e) {
+        const int k = eig_keys[e];
+        if (k < 0 || k >= K) {
+            if (msg) *msg = "eigen key index out of range";
+            return 1;
+        }
+        const double *ek = E + (size_t)k * M;
+        // diag(e_key) Td^T, reference src/transition_bundle.cpp:19-20
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) A[(size_t)i * M + j] = ek[i] * T[(size_t)j * M + i];
+        double *de = d + (size_t)e * M;
+        if (host_eig_real_general(M, A.data(), P + (size_t)e * M * M, Pinv + (size_t)e * M * M, de, di.data(), msg)) return 1;
+        double sc = 0.0, im = 0.0;
+        for (int i = 0; i < M; ++i) {
+            sc = std::max(sc, std::hypot(de[i], di[i]));
+            im = std::max(im, std::fabs(di[i]));
+        }
+        scale[e] = sc;
+        for (int i = 0; i < M; ++i) d_scaled[(size_t)e * M + i] = de[i] / sc;
+        if (cplx) cplx[e] = im > 0.0;
+    }
+    return 0;
+}
+
+}  // namespace smcb

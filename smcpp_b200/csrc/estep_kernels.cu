@@ -1,0 +1,822 @@
+// smcpp_b200 -- CUDA kernels of the E-step (sm_100a).  See estep_kernels.cuh / DESIGN.md.
+#include "estep_kernels.cuh"
+
+#include <math.h>
+
+namespace smcb {
+
+constexpr int kSeqWarps = 4;     // warps (= chunks) per CTA in the recursion kernels
+constexpr int kStatThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// d^span for integer span >= 1 through the precomputed log|d| (the reference calls std::pow,
+// src/hmm.cpp:75; the relative difference is <= |span log d| * 2^-53).
+__device__ __forceinline__ double pow_span(double d, double logd, int span)
+{
+    if (d == 0.0) return 0.0;
+    double r = exp((double)span * logd);
+    return (d < 0.0 && (span & 1)) ? -r : r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: padded / transposed operand tables
+// ------------------------------------------------------------------------------------------------
+__global__ void k_setup(Model m, const double *pi_in, const double *T_in, const double *E_in, const double *P_in,
+                        const double *Pinv_in, const double *d_in, const double *dsc_in, const double *scale_in)
+{
+    const int M = m.M, Mp = m.Mp, K = m.K, NE = m.n_eig;
+    const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+    double *pi = const_cast<double *>(m.pi), *Td = const_cast<double *>(m.Td), *TdT = const_cast<double *>(m.TdT);
+    double *E = const_cast<double *>(m.E);
+    float *A32 = const_cast<float *>(m.A32);
+    for (long x = tid; x < Mp; x += nth) pi[x] = x < M ? pi_in[x] : 0.0;
+    for (long x = tid; x < (long)M * Mp; x += nth) {
+        int i = (int)(x / Mp), j = (int)(x % Mp);
+        Td[x] = j < M ? T_in[(long)i * M + j] : 0.0;      // Td(i,j)
+        TdT[x] = j < M ? T_in[(long)j * M + i] : 0.0;     // row i of TdT holds Td(.,i): TdT[i*Mp + j] = Td(j,i)
+    }
+    for (long x = tid; x < (long)K * Mp; x += nth) {
+        int k = (int)(x / Mp), j = (int)(x % Mp);
+        E[x] = j < M ? E_in[(long)k * M + j] : 0.0;
+    }
+    for (long x = tid; x < (long)K * M * Mp; x += nth) {
+        int j = (int)(x % Mp);
+        long ki = x / Mp;
+        int i = (int)(ki % M), k = (int)(ki / M);
+        // (diag(e_k) Td^T)(j,i) = e_k(j) Td(i,j) in double, then rounded to float: reference src/hmm.cpp:85-86
+        A32[x] = j < M ? (float)(E_in[(long)k * M + j] * T_in[(long)i * M + j]) : 0.0f;
+    }
+    double *P = const_cast<double *>(m.P), *PT = const_cast<double *>(m.PT), *Pinv = const_cast<double *>(m.Pinv),
+           *PinvT = const_cast<double *>(m.PinvT);
+    for (long x = tid; x < (long)NE * M * Mp; x += nth) {
+        int c = (int)(x % Mp);
+        long er = x / Mp;
+        int r = (int)(er % M), e = (int)(er / M);
+        const double *Pe = P_in + (long)e * M * M, *Pie = Pinv_in + (long)e * M * M;
+        P[x] = c < M ? Pe[(long)r * M + c] : 0.0;        // P(r,c)
+        PT[x] = c < M ? Pe[(long)c * M + r] : 0.0;       // PT[(e*M+a)*Mp + j] = P(j,a)
+        Pinv[x] = c < M ? Pie[(long)r * M + c] : 0.0;    // Pinv(r,c)
+        PinvT[x] = c < M ? Pie[(long)c * M + r] : 0.0;   // PinvT[(e*M+i)*Mp + a] = Pinv(a,i)
+    }
+    double *dsc = const_cast<double *>(m.dsc), *logd = const_cast<double *>(m.logd), *dr = const_cast<double *>(m.dr);
+    for (long x = tid; x < (long)NE * Mp; x += nth) {
+        int e = (int)(x / Mp), a = (int)(x % Mp);
+        double v = a < M ? dsc_in[(long)e * M + a] : 0.0;
+        dsc[x] = v;
+        logd[x] = v != 0.0 ? log(fabs(v)) : 0.0;
+        dr[x] = a < M ? d_in[(long)e * M + a] : 0.0;
+    }
+    double *scale = const_cast<double *>(m.scale), *logscale = const_cast<double *>(m.logscale);
+    for (long x = tid; x < NE; x += nth) {
+        scale[x] = scale_in[x];
+        logscale[x] = log(scale_in[x]);
+    }
+}
+
+void launch_setup(const Model &m, const double *pi_in, const double *T_in, const double *E_in, const double *P_in,
+                  const double *Pinv_in, const double *d_in, const double *dsc_in, const double *scale_in, cudaStream_t st)
+{
+    long work = (long)m.K * m.M * m.Mp;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    k_setup<<<blocks, 256, 0, st>>>(m, pi_in, T_in, E_in, P_in, Pinv_in, d_in, dsc_in, scale_in);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward recursion: one warp per chunk, lane owns states j = lane + 32 r
+// ------------------------------------------------------------------------------------------------
+// Eigen 3.3.3 float sum() order (LinearVectorizedTraversal, SSE packets of 4, two accumulators), which
+// is what `alpha_hat.col(ell).sum()` compiles to in the reference (src/hmm.cpp:87).
+__device__ __forceinline__ float eigen_sum_f32(const float *v, int M)
+{
+    const int n4 = M >> 2, n8 = M >> 3;
+    float r;
+    if (n4) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(v);
+        float4 p0 = v4[0];
+        if (n4 > 1) {
+            float4 p1 = v4[1];
+            for (int q = 1; q < n8; ++q) {
+                float4 a = v4[2 * q], b = v4[2 * q + 1];
+                p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+                p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
+            }
+            p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
+            if (n4 > 2 * n8) {
+                float4 a = v4[2 * n8];
+                p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+            }
+        }
+        r = __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
+        for (int i = n4 * 4; i < M; ++i) r = __fadd_rn(r, v[i]);
+    } else {
+        r = v[0];
+        for (int i = 1; i < M; ++i) r = __fadd_rn(r, v[i]);
+    }
+    return r;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Work w, int pass)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kSeqWarps + warp;
+    if (c >= p.n_chunks) return;  // warp-uniform; the kernel has no CTA-wide barrier
+    const int M = m.M, Mp = m.Mp;
+    double *xd = reinterpret_cast<double *>(smem_raw) + warp * Mp;
+    float *xf = reinterpret_cast<float *>(smem_raw + (size_t)kSeqWarps * Mp * sizeof(double)) + warp * Mp;
+
+    const int t = p.ch_contig[c], s = p.ch_start[c], len = p.ch_len[c];
+    const int64_t g0 = p.blk_off[t];
+    const int cl = c - p.chunk_off[t];
+    float *acol = w.alpha + (p.col_off[t] + (int64_t)cl * (p.chunk_blocks + 1)) * Mp;
+
+    float x[R];
+    int b0;
+    if (pass == 0) {
+        b0 = s - p.burn_in;
+        if (b0 < 0) b0 = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = (float)m.pi[lane + 32 * r];  // src/hmm.cpp:59
+    } else {
+        if (!w.fwd_flag[c]) return;
+        b0 = s;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = w.end_alpha_prev[(size_t)(c - 1) * Mp + lane + 32 * r];
+    }
+    if (b0 == s) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            acol[lane + 32 * r] = x[r];
+            w.start_used[(size_t)c * Mp + lane + 32 * r] = x[r];
+        }
+    }
+    double llsum = 0.0;
+    const int bend = s + len;
+    for (int b = b0; b < bend; ++b) {
+        const int span = p.span[g0 + b];
+        const int k = p.key[g0 + b];
+        const int e = span > 1 ? m.eig_of_key[k] : -1;
+        double logc;
+        float sf = 0.f;
+        if (e >= 0) {
+            // a = P_r (d~^span o (Pinv_r alpha_prev)), double; src/hmm.cpp:74-80
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xd[lane + 32 * r] = (double)x[r];
+            __syncwarp();
+            double u[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) u[r] = 0.0;
+            const double *PinvT = m.PinvT + (size_t)e * M * Mp;
+            for (int i = 0; i < M; ++i) {
+                const double xi = xd[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) u[r] = fma(__ldg(PinvT + (size_t)i * Mp + lane + 32 * r), xi, u[r]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = lane + 32 * r;
+                xd[j] = pow_span(m.dsc[(size_t)e * Mp + j], m.logd[(size_t)e * Mp + j], span) * u[r];
+            }
+            __syncwarp();
+            double a[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) a[r] = 0.0;
+            const double *PT = m.PT + (size_t)e * M * Mp;
+            for (int i = 0; i < M; ++i) {
+                const double gi = xd[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) a[r] = fma(__ldg(PT + (size_t)i * Mp + lane + 32 * r), gi, a[r]);
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) part += a[r];
+            const double ssum = warp_sum(part);
+            logc = log(ssum) + (double)span * m.logscale[e];
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[r] = (float)(a[r] / ssum);
+        } else {
+            // float GEMV with the float-rounded step matrix, k-sequential axpy order; src/hmm.cpp:85-89
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xf[lane + 32 * r] = x[r];
+            __syncwarp();
+            float y[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) y[r] = 0.f;
+            const float *A = m.A32 + (size_t)k * M * Mp;
+            for (int i = 0; i < M; ++i) {
+                const float xi = xf[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[r] = __fadd_rn(y[r], __fmul_rn(xi, __ldg(A + (size_t)i * Mp + lane + 32 * r)));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xf[lane + 32 * r] = y[r];
+            __syncwarp();
+            sf = eigen_sum_f32(xf, M);
+            logc = log((double)sf);
+#pragma unroll
+            for (int r = 0; r < R; ++r) x[r] = __fdiv_rn(y[r], sf);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (lane + 32 * r < M && x[r] < 1e-10f) x[r] = 1e-10f;  // src/hmm.cpp:92-94
+        if (b >= s) {
+            float *col = acol + (size_t)(b - s + 1) * Mp;
+#pragma unroll
+            for (int r = 0; r < R; ++r) col[lane + 32 * r] = x[r];
+            llsum += logc;
+            if (e < 0 && lane == 0) w.cnorm[g0 + b] = sf;
+        } else if (b == s - 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acol[lane + 32 * r] = x[r];
+                w.start_used[(size_t)c * Mp + lane + 32 * r] = x[r];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) w.end_alpha[(size_t)c * Mp + lane + 32 * r] = x[r];
+    if (lane == 0) w.ll_chunk[c] = llsum;
+}
+
+void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
+{
+    const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
+    const size_t smem = (size_t)kSeqWarps * m.Mp * (sizeof(double) + sizeof(float));
+    switch (m.Mp / 32) {
+    case 1: k_forward<1><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    case 2: k_forward<2><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    case 3: k_forward<3><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    default: k_forward<4><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    }
+}
+
+__global__ void k_check_forward(Model m, Plan p, Work w, float tol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    uint8_t flag = 0;
+    if (c != p.chunk_off[p.ch_contig[c]]) {
+        const float *a = w.start_used + (size_t)c * m.Mp, *b = w.end_alpha + (size_t)(c - 1) * m.Mp;
+        float mx = 0.f, df = 0.f;
+        for (int j = 0; j < m.M; ++j) {
+            mx = fmaxf(mx, fabsf(b[j]));
+            df = fmaxf(df, fabsf(a[j] - b[j]));
+        }
+        const float rel = mx > 0.f ? df / mx : df;
+        flag = rel > tol;
+        if (rel > 0.f) atomicMax(&w.counters[2], __float_as_int(rel));
+    }
+    w.fwd_flag[c] = flag;
+    if (flag) atomicAdd(&w.counters[0], 1);
+}
+
+void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st)
+{
+    k_check_forward<<<(p.n_chunks + 127) / 128, 128, 0, st>>>(m, p, w, tol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward recursion (beta only; the statistics are accumulated block-parallel in k_stats)
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Work w, int pass)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kSeqWarps + warp;
+    if (c >= p.n_chunks) return;
+    const int M = m.M, Mp = m.Mp;
+    double *xd = reinterpret_cast<double *>(smem_raw) + warp * Mp;
+
+    const int t = p.ch_contig[c], s = p.ch_start[c], len = p.ch_len[c];
+    const int64_t g0 = p.blk_off[t];
+    const int L = (int)(p.blk_off[t + 1] - g0);
+    const int bend = s + len;
+    double beta[R];
+    int b1;
+    if (pass == 0) {
+        b1 = bend + p.burn_in;
+        if (b1 > L || bend == L) b1 = L;
+#pragma unroll
+        for (int r = 0; r < R; ++r) beta[r] = lane + 32 * r < M ? 1.0 : 0.0;  // src/hmm.cpp:97
+    } else {
+        if (!w.bwd_flag[c]) return;
+        b1 = bend;
+#pragma unroll
+        for (int r = 0; r < R; ++r) beta[r] = w.beta_out_prev[(size_t)(c + 1) * Mp + lane + 32 * r];
+    }
+    for (int b = b1 - 1; b >= s; --b) {
+        if (b == bend - 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) w.bstart_used[(size_t)c * Mp + lane + 32 * r] = beta[r];
+        }
+        const bool storing = b < bend;
+        const int span = p.span[g0 + b];
+        const int k = p.key[g0 + b];
+        const int e = span > 1 ? m.eig_of_key[k] : -1;
+        double *bv = w.bvec + (size_t)(g0 + b) * Mp;
+        double nb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) nb[r] = 0.0;
+        if (e >= 0) {
+            // beta <- Pinv_r^T (d~^span o (P_r^T beta)); src/hmm.cpp:123-127 (the log/exp there only rescales)
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xd[lane + 32 * r] = beta[r];
+            __syncwarp();
+            double wv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) wv[r] = 0.0;
+            const double *P = m.P + (size_t)e * M * Mp;
+            for (int i = 0; i < M; ++i) {
+                const double bi = xd[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) wv[r] = fma(__ldg(P + (size_t)i * Mp + lane + 32 * r), bi, wv[r]);
+            }
+            if (storing) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) bv[lane + 32 * r] = wv[r];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = lane + 32 * r;
+                xd[j] = pow_span(m.dsc[(size_t)e * Mp + j], m.logd[(size_t)e * Mp + j], span) * wv[r];
+            }
+            __syncwarp();
+            const double *Pinv = m.Pinv + (size_t)e * M * Mp;
+            for (int a = 0; a < M; ++a) {
+                const double ga = xd[a];
+#pragma unroll
+                for (int r = 0; r < R; ++r) nb[r] = fma(__ldg(Pinv + (size_t)a * Mp + lane + 32 * r), ga, nb[r]);
+            }
+        } else {
+            // beta <- Td (e_k o beta); src/hmm.cpp:139
+            if (storing) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) bv[lane + 32 * r] = beta[r];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) xd[lane + 32 * r] = m.E[(size_t)k * Mp + lane + 32 * r] * beta[r];
+            __syncwarp();
+            for (int j = 0; j < M; ++j) {
+                const double tj = xd[j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) nb[r] = fma(__ldg(m.TdT + (size_t)j * Mp + lane + 32 * r), tj, nb[r]);
+            }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) part += nb[r];
+        const double ssum = warp_sum(part);
+#pragma unroll
+        for (int r = 0; r < R; ++r) beta[r] = nb[r] / ssum;  // src/hmm.cpp:142
+    }
+    if (b1 == bend && len == 0) {  // cannot happen (chunks are non-empty); keeps bstart_used defined
+#pragma unroll
+        for (int r = 0; r < R; ++r) w.bstart_used[(size_t)c * Mp + lane + 32 * r] = beta[r];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) w.beta_out[(size_t)c * Mp + lane + 32 * r] = beta[r];
+}
+
+void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
+{
+    const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
+    const size_t smem = (size_t)kSeqWarps * m.Mp * sizeof(double);
+    switch (m.Mp / 32) {
+    case 1: k_backward<1><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    case 2: k_backward<2><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    case 3: k_backward<3><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    default: k_backward<4><<<blocks, kSeqWarps * 32, smem, st>>>(m, p, w, pass); break;
+    }
+}
+
+__global__ void k_check_backward(Model m, Plan p, Work w, double tol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    uint8_t flag = 0;
+    const int t = p.ch_contig[c];
+    if (c + 1 != p.chunk_off[t + 1]) {
+        const double *a = w.bstart_used + (size_t)c * m.Mp, *b = w.beta_out + (size_t)(c + 1) * m.Mp;
+        double mx = 0., df = 0.;
+        for (int j = 0; j < m.M; ++j) {
+            mx = fmax(mx, fabs(b[j]));
+            df = fmax(df, fabs(a[j] - b[j]));
+        }
+        const double rel = mx > 0. ? df / mx : df;
+        flag = rel > tol;
+        if (rel > 0.) atomicMax(&w.counters[3], __float_as_int((float)rel));
+    }
+    w.bwd_flag[c] = flag;
+    if (flag) atomicAdd(&w.counters[1], 1);
+}
+
+void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st)
+{
+    k_check_backward<<<(p.n_chunks + 127) / 128, 128, 0, st>>>(m, p, w, tol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics: block-parallel accumulation per slab.
+//   span-1 block l (key k):  p = alpha_l . beta_l ;  gamma_sums[k] += alpha_l o beta_l / p
+//                            X += alpha_{l-1} (beta_l o e_k)^T / (c_l p)                   src/hmm.cpp:134-138
+//   span>1 block l (eigen e): u = Pinv_r alpha_{l-1}, w = P_r^T beta_l, C = 1/(scale sum_a d~_a^s u_a w_a)
+//                            R_e += C [(u o d~^s) w^T - u (w o d~^s)^T],  D_e += C s d~^(s-1) o u o w
+//   which is the rank-2 (displacement) form of C (u w^T) o sq_span of src/hmm.cpp:113-122; k_finalize
+//   divides R_e by (d~_a - d~_b) and maps the eigenbasis accumulators back to state space once per key.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int stats_tile_blocks(int Mp) { return Mp > 64 ? 16 : 32; }
+
+int stats_smem_bytes(const Model &m)
+{
+    const int NB = stats_tile_blocks(m.Mp);
+    size_t dense = (size_t)3 * NB * m.Mp * 8 + (size_t)m.K * m.Mp * 8;
+    size_t eig = (size_t)5 * NB * m.Mp * 8;
+    size_t tail = (size_t)NB * 16;
+    return (int)((dense > eig ? dense : eig) + tail);
+}
+
+template <int TM>
+__global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = m.M, Mp = m.Mp, K = m.K;
+    const int NB = stats_tile_blocks(Mp);
+    const int slab = blockIdx.x;
+    const int t = p.sl_contig[slab], s0 = p.sl_start[slab], n = p.sl_len[slab];
+    const uint32_t mask = p.sl_mask[slab];
+    const int64_t g0 = p.blk_off[t];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ty = tid >> 4, tx = tid & 15;
+    constexpr int NW = kStatThreads / 32;
+    constexpr int R = TM / 2;  // Mp / 32
+
+    double *S0 = reinterpret_cast<double *>(smem_raw);  // [NB][Mp]
+    double *S1 = S0 + (size_t)NB * Mp;
+    double *S2 = S1 + (size_t)NB * Mp;
+    double *S3 = S2 + (size_t)NB * Mp;                   // eigen pass only
+    double *S4 = S3 + (size_t)NB * Mp;                   // eigen pass only
+    // tail (valid flags / keys) sits after the larger of the two layouts
+    const size_t dense_b = (size_t)3 * NB * Mp * 8 + (size_t)K * Mp * 8, eig_b = (size_t)5 * NB * Mp * 8;
+    int *tvalid = reinterpret_cast<int *>(smem_raw + (dense_b > eig_b ? dense_b : eig_b));
+    int *tkey = tvalid + NB;
+    double *gs = S3;  // dense pass only: [K][Mp] (aliases S3/S4 region and beyond)
+
+    const int Lc = p.chunk_blocks;
+    const int64_t colbase = p.col_off[t];
+    auto alpha_col = [&](int b) -> const float * {  // column holding alpha_hat_{b} "before block b" (i.e. alpha_{l-1} for l=b+1)
+        const int cb = b / Lc;
+        return w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (b - cb * Lc)) * Mp;
+    };
+
+    // ---------------- span-1 blocks
+    if (mask & 1u) {
+        double acc[TM][TM];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
+        for (int x = tid; x < K * Mp; x += kStatThreads) gs[x] = 0.0;
+        __syncthreads();
+        for (int tile0 = 0; tile0 < n; tile0 += NB) {
+            for (int bq = warp; bq < NB; bq += NW) {
+                const int b = s0 + tile0 + bq;
+                int valid = 0, k = 0;
+                if (tile0 + bq < n && p.span[g0 + b] == 1) {
+                    valid = 1;
+                    k = p.key[g0 + b];
+                    const float *ap = alpha_col(b), *ac = ap + Mp;
+                    const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
+                    double be[R], acur[R], part = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        be[r] = bv[lane + 32 * r];
+                        acur[r] = (double)ac[lane + 32 * r];
+                        part += acur[r] * be[r];
+                    }
+                    const double pp = warp_sum(part);                 // p = sum(alpha_l o beta)
+                    const double cd = exp(log((double)w.cnorm[g0 + b]));  // exp(log_c(l)), src/hmm.cpp:137
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int j = lane + 32 * r;
+                        S0[(size_t)bq * Mp + j] = (double)ap[j];
+                        S1[(size_t)bq * Mp + j] = be[r] * m.E[(size_t)k * Mp + j] / cd / pp;
+                        S2[(size_t)bq * Mp + j] = acur[r] * be[r] / pp;
+                    }
+                }
+                if (lane == 0) { tvalid[bq] = valid; tkey[bq] = k; }
+            }
+            __syncthreads();
+            if (tid < Mp) {
+                for (int bq = 0; bq < NB; ++bq)
+                    if (tvalid[bq]) gs[(size_t)tkey[bq] * Mp + tid] += S2[(size_t)bq * Mp + tid];
+            }
+            for (int bq = 0; bq < NB; ++bq) {
+                if (!tvalid[bq]) continue;
+                double av[TM], bvv[TM];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = S0[(size_t)bq * Mp + ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < TM; ++j) bvv[j] = S1[(size_t)bq * Mp + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TM; ++j) acc[i][j] = fma(av[i], bvv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+        double *Xp = w.Xpart + (size_t)slab * Mp * Mp;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TM; ++j) Xp[(size_t)(ty + 16 * i) * Mp + tx + 16 * j] = acc[i][j];
+        double *gp = w.gspart + (size_t)slab * K * Mp;
+        for (int x = tid; x < K * Mp; x += kStatThreads) gp[x] = gs[x];
+        __syncthreads();
+    }
+
+    // ---------------- span>1 blocks, one pass per eigen key present in the slab
+    for (int e = 0; e < m.n_eig; ++e) {
+        if (!(mask & (2u << e))) continue;
+        double acc[TM][TM];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
+        double dacc = 0.0;
+        const double *PinvT = m.PinvT + (size_t)e * M * Mp;
+        const double sc = m.scale[e];
+        for (int tile0 = 0; tile0 < n; tile0 += NB) {
+            for (int bq = warp; bq < NB; bq += NW) {
+                const int b = s0 + tile0 + bq;
+                int valid = 0;
+                if (tile0 + bq < n) {
+                    const int span = p.span[g0 + b];
+                    if (span > 1 && m.eig_of_key[p.key[g0 + b]] == e) {
+                        valid = 1;
+                        const float *ap = alpha_col(b);
+                        const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
+                        double *arow = S0 + (size_t)bq * Mp;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) arow[lane + 32 * r] = (double)ap[lane + 32 * r];
+                        __syncwarp();
+                        double u[R], wv[R], pw[R], part = 0.0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) u[r] = 0.0;
+                        for (int i = 0; i < M; ++i) {
+                            const double ai = arow[i];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) u[r] = fma(__ldg(PinvT + (size_t)i * Mp + lane + 32 * r), ai, u[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int j = lane + 32 * r;
+                            wv[r] = bv[j];
+                            pw[r] = pow_span(m.dsc[(size_t)e * Mp + j], m.logd[(size_t)e * Mp + j], span);
+                            part += pw[r] * u[r] * wv[r];
+                        }
+                        const double dot = warp_sum(part);
+                        const double C = 1.0 / (sc * dot);
+                        __syncwarp();
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int j = lane + 32 * r;
+                            const double dj = m.dsc[(size_t)e * Mp + j];
+                            const double y = C * wv[r];
+                            S0[(size_t)bq * Mp + j] = u[r] * pw[r];   // x
+                            S1[(size_t)bq * Mp + j] = y;              // y
+                            S2[(size_t)bq * Mp + j] = u[r];           // u
+                            S3[(size_t)bq * Mp + j] = y * pw[r];      // z
+                            S4[(size_t)bq * Mp + j] = dj != 0.0 ? y * u[r] * (double)span * (pw[r] / dj) : 0.0;  // diagonal
+                        }
+                    }
+                }
+                if (lane == 0) tvalid[bq] = valid;
+            }
+            __syncthreads();
+            if (tid < Mp) {
+                for (int bq = 0; bq < NB; ++bq)
+                    if (tvalid[bq]) dacc += S4[(size_t)bq * Mp + tid];
+            }
+            for (int bq = 0; bq < NB; ++bq) {
+                if (!tvalid[bq]) continue;
+                double xv[TM], uv[TM], yv[TM], zv[TM];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    xv[i] = S0[(size_t)bq * Mp + ty + 16 * i];
+                    uv[i] = S2[(size_t)bq * Mp + ty + 16 * i];
+                }
+#pragma unroll
+                for (int j = 0; j < TM; ++j) {
+                    yv[j] = S1[(size_t)bq * Mp + tx + 16 * j];
+                    zv[j] = S3[(size_t)bq * Mp + tx + 16 * j];
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TM; ++j) acc[i][j] = fma(-uv[i], zv[j], fma(xv[i], yv[j], acc[i][j]));
+            }
+            __syncthreads();
+        }
+        double *Rp = w.Rpart + ((size_t)slab * m.n_eig + e) * Mp * Mp;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TM; ++j) Rp[(size_t)(ty + 16 * i) * Mp + tx + 16 * j] = acc[i][j];
+        if (tid < Mp) w.dpart[((size_t)slab * m.n_eig + e) * Mp + tid] = dacc;
+        __syncthreads();
+    }
+}
+
+void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+{
+    const int smem = stats_smem_bytes(m);
+    switch (m.Mp / 32) {
+    case 1:
+        cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_stats<2><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
+        break;
+    case 2:
+        cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_stats<4><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
+        break;
+    case 3:
+        cudaFuncSetAttribute(k_stats<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_stats<6><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
+        break;
+    default:
+        cudaFuncSetAttribute(k_stats<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        k_stats<8><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
+        break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: one CTA per contig
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
+{
+    const int M = m.M, Mp = m.Mp, K = m.K, NE = m.n_eig;
+    const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const int sl0 = p.slab_off[t], sl1 = p.slab_off[t + 1];
+    const size_t MM = (size_t)Mp * Mp;
+    double *X = w.scratch + (size_t)t * 3 * MM, *A = X + MM, *G = A + MM;
+    __shared__ uint32_t cmask;
+    if (tid == 0) {
+        uint32_t mk = 0;
+        for (int s = sl0; s < sl1; ++s) mk |= p.sl_mask[s];
+        cmask = mk;
+    }
+    __syncthreads();
+    const uint32_t mask = cmask;
+    // X = sum of the span-1 partials
+    for (size_t x = tid; x < MM; x += nth) {
+        double acc = 0.0;
+        for (int s = sl0; s < sl1; ++s)
+            if (p.sl_mask[s] & 1u) acc += w.Xpart[(size_t)s * MM + x];
+        X[x] = acc;
+    }
+    // gamma_sums = sum of the span-1 partials (unpadded output [K][M])
+    double *gso = w.gamma_sums + (size_t)t * K * M;
+    for (int x = tid; x < K * M; x += nth) {
+        const int k = x / M, j = x % M;
+        double acc = 0.0;
+        for (int s = sl0; s < sl1; ++s)
+            if (p.sl_mask[s] & 1u) acc += w.gspart[((size_t)s * K + k) * Mp + j];
+        gso[x] = acc;
+    }
+    __syncthreads();
+    for (int e = 0; e < NE; ++e) {
+        if (!(mask & (2u << e))) continue;
+        const double *dsc = m.dsc + (size_t)e * Mp, *dr = m.dr + (size_t)e * Mp;
+        const double *P = m.P + (size_t)e * M * Mp, *Pinv = m.Pinv + (size_t)e * M * Mp;
+        const int ke = m.key_of_eig[e];
+        // Acc(a,b) = R(a,b) / (d~_a - d~_b), Acc(a,a) = D(a)
+        for (size_t x = tid; x < MM; x += nth) {
+            const int a = (int)(x / Mp), b = (int)(x % Mp);
+            double acc = 0.0;
+            if (a < M && b < M) {
+                if (a == b) {
+                    for (int s = sl0; s < sl1; ++s)
+                        if (p.sl_mask[s] & (2u << e)) acc += w.dpart[((size_t)s * NE + e) * Mp + a];
+                } else {
+                    for (int s = sl0; s < sl1; ++s)
+                        if (p.sl_mask[s] & (2u << e)) acc += w.Rpart[((size_t)s * NE + e) * MM + x];
+                    acc /= dsc[a] - dsc[b];
+                }
+            }
+            A[x] = acc;
+        }
+        __syncthreads();
+        // G = Acc Pinv_r
+        for (size_t x = tid; x < MM; x += nth) {
+            const int a = (int)(x / Mp), i = (int)(x % Mp);
+            double acc = 0.0;
+            if (a < M && i < M)
+                for (int b = 0; b < M; ++b) acc = fma(A[(size_t)a * Mp + b], Pinv[(size_t)b * Mp + i], acc);
+            G[x] = acc;
+        }
+        __syncthreads();
+        // X += (P_r G) diag(e_key);  gamma_sums[key] += diag(P_r diag(d_r) G)
+        for (size_t x = tid; x < MM; x += nth) {
+            const int i = (int)(x / Mp), j = (int)(x % Mp);
+            if (i < M && j < M) {
+                double acc = 0.0;
+                for (int a = 0; a < M; ++a) acc = fma(P[(size_t)i * Mp + a], G[(size_t)a * Mp + j], acc);
+                X[x] += acc * m.E[(size_t)ke * Mp + j];
+            }
+        }
+        for (int i = tid; i < M; i += nth) {
+            double acc = 0.0;
+            for (int a = 0; a < M; ++a) acc = fma(P[(size_t)i * Mp + a] * dr[a], G[(size_t)a * Mp + i], acc);
+            gso[(size_t)ke * M + i] += acc;
+        }
+        __syncthreads();
+    }
+    // xisum = max(X o Td, 1e-20); src/hmm.cpp:151-152
+    double *xo = w.xisum + (size_t)t * M * M;
+    for (int x = tid; x < M * M; x += nth) {
+        const int i = x / M, j = x % M;
+        const double v = X[(size_t)i * Mp + j] * m.Td[(size_t)i * Mp + j];
+        xo[x] = v < 1e-20 ? 1e-20 : v;
+    }
+    // gamma0 = alpha_hat_0 o beta_0; src/hmm.cpp:150
+    const int c0 = p.chunk_off[t];
+    const float *a0 = w.alpha + p.col_off[t] * Mp;
+    for (int j = tid; j < M; j += nth) w.gamma0[(size_t)t * M + j] = (double)a0[j] * w.beta_out[(size_t)c0 * Mp + j];
+    // ll = sum of the chunk log-normalisers (warp 0, fixed order)
+    if (tid < 32) {
+        double acc = 0.0;
+        for (int c = c0 + tid; c < p.chunk_off[t + 1]; c += 32) acc += w.ll_chunk[c];
+        acc = warp_sum(acc);
+        if (tid == 0) w.ll[t] = acc;
+    }
+}
+
+__global__ void k_reduce(Model m, Plan p, Work w)
+{
+    const int M = m.M, K = m.K, C = p.n_contigs;
+    const long n = 1 + M + (long)M * M + (long)K * M;
+    for (long x = blockIdx.x * (long)blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        if (x == 0) {
+            for (int t = 0; t < C; ++t) acc += w.ll[t];
+        } else if (x < 1 + M) {
+            for (int t = 0; t < C; ++t) acc += w.gamma0[(size_t)t * M + (x - 1)];
+        } else if (x < 1 + M + (long)M * M) {
+            for (int t = 0; t < C; ++t) acc += w.xisum[(size_t)t * M * M + (x - 1 - M)];
+        } else {
+            for (int t = 0; t < C; ++t) acc += w.gamma_sums[(size_t)t * K * M + (x - 1 - M - (long)M * M)];
+        }
+        w.reduced[x] = acc;
+    }
+}
+
+void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+{
+    k_finalize<<<p.n_contigs, 256, 0, st>>>(m, p, w);
+    const long n = 1 + m.M + (long)m.M * m.M + (long)m.K * m.M;
+    k_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(m, p, w);
+}
+
+// debug tap: contiguous [L+1][M] alpha_hat of one contig
+__global__ void k_gather_alpha(Model m, Plan p, Work w, int t, float *out)
+{
+    const int M = m.M, Mp = m.Mp, Lc = p.chunk_blocks;
+    const int64_t L = p.blk_off[t + 1] - p.blk_off[t];
+    const int64_t n = (L + 1) * M;
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = x / M;
+        const int j = (int)(x % M);
+        int64_t col;
+        if (l == 0) col = 0;
+        else {
+            const int64_t b = l - 1, cb = b / Lc;
+            col = cb * (Lc + 1) + (b - cb * Lc) + 1;
+        }
+        out[x] = w.alpha[(p.col_off[t] + col) * Mp + j];
+    }
+}
+
+void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st)
+{
+    k_gather_alpha<<<592, 256, 0, st>>>(m, p, w, contig, out);
+}
+
+}  // namespace smcb

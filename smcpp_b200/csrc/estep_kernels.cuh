@@ -1,0 +1,106 @@
+// smcpp_b200 -- device side of the E-step (sm_100a).
+//
+// Pipeline per E-step:
+//   k_setup      : padded / transposed operand tables, fl32(e_k(j) * Td(i,j)) step matrices
+//   k_forward    : one warp per chunk, scaled forward recursion with the reference's float semantics
+//                  (reference src/hmm.cpp:58-96); chunk starts come from a burn-in over the preceding
+//                  blocks and are verified against the previous chunk's end (k_check_forward)
+//   k_backward   : one warp per chunk, beta recursion (reference src/hmm.cpp:97-149, recursion part)
+//   k_stats      : block-parallel accumulation of the xi / gamma sufficient statistics
+//   k_finalize   : per-contig reduction, eigenbasis -> state basis, "o Td", floors (src/hmm.cpp:150-152)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smcb {
+
+constexpr int kMaxMp = 128;       // padded state count limit (M <= 128)
+constexpr int kMaxEig = 30;       // eigen keys representable in a slab type mask
+
+// Per-E-step operands on the device.  All matrices are padded to Mp = 32*ceil(M/32) in the fast
+// (lane) dimension; pads are zero.
+struct Model {
+    int M, Mp, K, n_eig;
+    const double *pi;        // [Mp]
+    const double *Td;        // [M][Mp]   Td[i*Mp + j] = Td(i,j)
+    const double *TdT;       // [M][Mp]   TdT[j*Mp + i] = Td(i,j)
+    const float *A32;        // [K][M][Mp] A32[(k*M + i)*Mp + j] = fl32(e_k(j) * Td(i,j))
+    const double *E;         // [K][Mp]
+    const int *eig_of_key;   // [K]  -1 or eigen index
+    const int *key_of_eig;   // [n_eig]
+    const double *P;         // [n_eig][M][Mp]  P[(e*M + i)*Mp + a] = P_r(i,a)
+    const double *PT;        // [n_eig][M][Mp]  PT[(e*M + a)*Mp + j] = P_r(j,a)
+    const double *Pinv;      // [n_eig][M][Mp]  Pinv[(e*M + a)*Mp + i] = Pinv_r(a,i)
+    const double *PinvT;     // [n_eig][M][Mp]  PinvT[(e*M + i)*Mp + a] = Pinv_r(a,i)
+    const double *dsc;       // [n_eig][Mp] d_r / scale
+    const double *logd;      // [n_eig][Mp] log|dsc|
+    const double *dr;        // [n_eig][Mp] d_r
+    const double *scale;     // [n_eig]
+    const double *logscale;  // [n_eig]
+};
+
+// Static per-dataset layout (set_contigs) + per-plan chunking.
+struct Plan {
+    int n_contigs, n_chunks, n_slabs;
+    int chunk_blocks, burn_in, slab_blocks;
+    int64_t total_blocks;
+    // per block (concatenated over contigs)
+    const int32_t *span;     // [total]
+    const uint16_t *key;     // [total]
+    // per contig
+    const int64_t *blk_off;  // [C+1] first global block of contig
+    const int64_t *col_off;  // [C]   first alpha column of contig (chunk c at col_off + c*(chunk_blocks+1))
+    const int32_t *chunk_off;// [C+1] first chunk of contig
+    const int32_t *slab_off; // [C+1]
+    // per chunk
+    const int32_t *ch_contig;// [n_chunks]
+    const int32_t *ch_start; // [n_chunks] first block (within contig)
+    const int32_t *ch_len;   // [n_chunks]
+    // per slab
+    const int32_t *sl_contig;// [n_slabs]
+    const int32_t *sl_start; // [n_slabs]
+    const int32_t *sl_len;   // [n_slabs]
+    const uint32_t *sl_mask; // [n_slabs] bit0: has span-1 blocks; bit 1+e: has span>1 blocks of eigen key e
+};
+
+// Work buffers.
+struct Work {
+    float *alpha;            // [n_cols][Mp]  chunk-local alpha_hat columns (column 0 of a chunk = its start)
+    float *cnorm;            // [total]       float forward normaliser of span-1 blocks (hmm.cpp:87)
+    double *bvec;            // [total][Mp]   beta_l (span 1) or w_l = P_r^T beta_l (span > 1)
+    float *start_used;       // [n_chunks][Mp]
+    float *end_alpha;        // [n_chunks][Mp]
+    float *end_alpha_prev;   // [n_chunks][Mp] snapshot of the previous sweep
+    double *ll_chunk;        // [n_chunks]
+    double *bstart_used;     // [n_chunks][Mp] beta the chunk started from (at its right end)
+    double *beta_out;        // [n_chunks][Mp] beta at the chunk's left end
+    double *beta_out_prev;   // [n_chunks][Mp]
+    uint8_t *fwd_flag;       // [n_chunks] 1 = must be (re)run in the next sweep
+    uint8_t *bwd_flag;       // [n_chunks]
+    int *counters;           // [8]: 0 fwd flagged, 1 bwd flagged, 2 fwd max mismatch (float bits), 3 bwd max mismatch bits(hi) ..
+    double *Xpart;           // [n_slabs][Mp*Mp]
+    double *Rpart;           // [n_slabs][n_eig][Mp*Mp]
+    double *dpart;           // [n_slabs][n_eig][Mp]
+    double *gspart;          // [n_slabs][K][Mp]
+    double *scratch;         // [C][3][Mp*Mp]
+    // outputs (device)
+    double *ll;              // [C]
+    double *xisum;           // [C][M][M]
+    double *gamma0;          // [C][M]
+    double *gamma_sums;      // [C][K][M]
+    double *reduced;         // [1 + M + M*M + K*M]
+};
+
+// (launch_setup fills the tables the Model's const pointers refer to)
+void launch_setup(const Model &m, const double *pi_in, const double *T_in, const double *E_in, const double *P_in,
+                  const double *Pinv_in, const double *d_in, const double *dsc_in, const double *scale_in, cudaStream_t st);
+void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
+void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
+void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
+void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);
+void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
+void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
+void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st);
+int stats_smem_bytes(const Model &m);
+
+}  // namespace smcb
