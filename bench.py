@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""E-step throughput benchmark (BASELINE.json metric: observation-blocks/s at M = 32 on 1/2/4/8 GPUs).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # our arm, one process per GPU
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  # the reference's CPU path (oracle/_ref)
+
+A "step" is one E-step (InferenceManager::Estep with clean dirty flags) over the workload:
+config 3 of BASELINE.json -- 22 synthetic contigs x 10^6 RLE blocks, M = 32, n = 20 -- with the contigs
+sharded over the ranks (strong scaling) and one NCCL SUM all-reduce of the packed statistics per step.
+Model inputs (pi, transition, emission table) come from tests/golden/model_C3.npz, which the unmodified
+reference produced for this exact workload; observations are synthetic (smcpp_b200/synth.py).
+
+`value`  : blocks/s with everything resident in HBM (per-step inputs included), wall time of K steps
+           bracketed by barrier + synchronize, max over ranks.
+`e2e`    : the same through the host-facing C ABI call (host buffers: per-step inputs H2D, all per-contig
+           results D2H inside the timed region) + the all-reduce.
+`roofline`: recursion kernels (k_forward || k_backward, the dominant phase) against the measured HBM peak,
+           algorithmic bytes of SURVEY 8d; `roofline_fp64` relates the algorithmic flops to the measured
+           FP64 FMA peak of this GPU, which is the bound that binds at M = 32.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from smcpp_b200 import parallel, synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_model(cfg):
+    z = np.load(os.path.join(GOLDEN, f"model_{cfg}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def workload_spec(cfg):
+    """(contigs, L, M, n, npop) of a BASELINE config without generating it."""
+    table = {"C1": (1, 10_000, 16, (4,), 1), "C2": (1, 1_000_000, 32, (10,), 1), "C3": (22, 1_000_000, 32, (20,), 1),
+             "C4": (2, 500_000, 32, (6, 6), 2)}
+    if cfg in table:
+        return table[cfg]
+    if cfg.startswith("C5-"):
+        return (1, 1_000_000, int(cfg[3:]), (10,), 1)
+    raise KeyError(cfg)
+
+
+def alg_bytes_per_block(M, P):
+    # obs row read in both passes + float alpha column written and read + log_c written and read
+    return 2 * 4 * (1 + 3 * P) + 2 * 4 * M + 2 * 8
+
+
+def alg_flops_per_block(M):
+    return 10 * M * M
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_arm(args, cfg, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref/ref_harness = the unmodified
+    reference sources) on the host cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return 0
+    from oracle import refrun
+    C, L, M, n, P = workload_spec(cfg)
+    cores = os.cpu_count() or 1
+    threads = min(C, cores)
+    sample_L = min(L, args.ref_sample_blocks)
+    w = synth.make_workload(cfg, C, sample_L, M, n, npop=P)
+    if not refrun.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness is not built on this box"}))
+        return 0
+    out = refrun.run(w, threads=threads, repeat=args.warmup + args.steps)
+    secs = out["estep_seconds"][args.warmup:]
+    t = float(np.sum(secs))
+    blocks = w.total_blocks * len(secs)
+    val = blocks / t
+    sample = f"{C} contigs x {sample_L} blocks (1/{max(1, L // sample_L)} of each contig), M={M}, {threads} OpenMP threads"
+    line = {"impl": "reference", "metric": "E-step observation-blocks/sec", "value": val, "unit": "blocks/s", "n_gpus": args.gpus,
+            "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (float alpha_hat storage)", "data": "synthetic",
+            "config": {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n}", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "blocks/s", "cores": threads, "kind": "reference", "sample": sample,
+                             "host_cores": cores},
+            "e2e": {"value": val, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--ref-sample-blocks", type=int, default=50_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = args.workload
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return reference_arm(args, cfg, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from smcpp_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (smcpp_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    C, L, M, n, P = workload_spec(cfg)
+    model = load_model(cfg)
+    K = model["keys"].shape[0]
+    owned = parallel.shard_contigs([L] * C, world)[rank]
+    contigs = [synth.make_contig(L, n, 1000 + c, P) for c in owned]
+    my_blocks = sum(c.shape[0] for c in contigs)
+    total_blocks = C * L
+
+    ctx = capi.Context(local_rank)
+    t0 = time.time()
+    if contigs:
+        ctx.set_contigs(contigs, P, model["keys"])
+    upload_s = time.time() - t0
+    nred = 1 + M + M * M + K * M
+    red = torch.zeros(nred, dtype=torch.float64, device="cuda")
+    eig = model   # the reference's eigensystems for this model (bit-identical inputs on both arms)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if contigs:
+            ctx.estep_device(model["pi"], model["T"], model["E"], eig, upload=False)
+            ctx.copy_reduced_to_device(red.data_ptr(), nred)
+        else:
+            red.zero_()
+        parallel.allreduce_sum_(red)
+
+    host_out = {}
+
+    def step_e2e():
+        if contigs:
+            o = ctx.estep(model["pi"], model["T"], model["E"], eig)       # H2D inputs, kernels, D2H results
+            host_out.update(o)
+            red.copy_(torch.from_numpy(o["reduced"]))
+        else:
+            red.zero_()
+        parallel.allreduce_sum_(red)
+        return red.cpu()
+
+    # ---- warm-up (also uploads the per-step inputs once for the resident arm)
+    if contigs:
+        ctx.estep_device(model["pi"], model["T"], model["E"], eig, upload=True)
+    for _ in range(args.warmup):
+        step_resident()
+    launches_per_step = ctx.stats()["kernel_launches"] if contigs else 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ms_rec, ms_tot = [], []
+    for _ in range(args.steps):
+        step_resident()
+        if contigs:
+            st = ctx.stats()
+            ms_rec.append(st["ms_forward"])
+            ms_tot.append(st["ms_total"])
+    barrier()
+    t_res = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ll_total = float(red[0].item())
+    # ---- end-to-end arm
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_res, t_e2e = float(tt[0]), float(tt[1])
+    value = total_blocks * args.steps / t_res
+    e2e = total_blocks * args.steps / t_e2e
+
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        rec_ms = float(np.mean(ms_rec)) if ms_rec else float("nan")
+        tot_ms = float(np.mean(ms_tot)) if ms_tot else float("nan")
+        ach = alg_bytes_per_block(M, P) * my_blocks / (rec_ms * 1e-3) / 1e9
+        fp64_peak = ctx.fp64_peak_tflops()
+        ach_f = alg_flops_per_block(M) * my_blocks / (tot_ms * 1e-3) / 1e12
+        h2d = 8 * (M + M * M + K * M + len(model["eig_scale"]) * (2 * M * M + 2 * M + 1))
+        d2h = 8 * (len(owned) * (1 + M + M * M + K * M) + nred)
+        line = {
+            "metric": "E-step observation-blocks/sec", "value": value, "unit": "blocks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64 (float alpha_hat storage, as the reference)", "data": "synthetic",
+            "config": {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n}, contigs sharded over ranks",
+                       "l2": "per-step working set (alpha_hat + beta vectors, %.1f GB on rank 0) exceeds L2; no flush needed"
+                             % (my_blocks * (4 * M + 8 * M + 10) / 1e9),
+                       "model_inputs": f"tests/golden/model_{cfg}.npz (reference do_dirty_work output)",
+                       "one_time_upload_s": upload_s},
+            "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
+            "e2e": {"value": e2e, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "k_forward || k_backward (recursions, rank 0)", "achieved": ach, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms},
+            "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
+                              "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
+                              "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},
+            "loglik": ll_total, "chunks": ctx.stats()["n_chunks"], "sweeps": [ctx.stats()["fwd_sweeps"], ctx.stats()["bwd_sweeps"]],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import refrun
+                if refrun.available():
+                    cores = os.cpu_count() or 1
+                    threads = min(C, cores)
+                    sL = min(L, args.ref_sample_blocks)
+                    w = synth.make_workload(cfg, C, sL, M, n, npop=P)
+                    o = refrun.run(w, threads=threads, repeat=2)
+                    s = float(o["estep_seconds"][-1])
+                    line["cpu_baseline"] = {"value": w.total_blocks / s, "unit": "blocks/s", "cores": threads, "kind": "reference",
+                                            "sample": f"{C} contigs x {sL} blocks, {threads} OpenMP threads of {cores} host cores",
+                                            "seconds": s}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "blocks/s", "cores": 0, "kind": "reference",
+                                            "sample": "oracle/_ref not built on this box"}
+            except Exception as ex:  # the baseline must never break the bench line
+                line["cpu_baseline"] = {"value": None, "unit": "blocks/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

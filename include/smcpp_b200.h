@@ -109,6 +109,10 @@ int smcpp_b200_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
  * 1 + M + M*M + K*M doubles, valid until the next estep(); lets the caller all-reduce it in place. */
 int smcpp_b200_reduced_device_ptr(smcpp_b200_ctx *ctx, void **ptr, int64_t *count);
 
+/* Copies that vector into caller-owned DEVICE memory on the same GPU (e.g. a torch tensor that is then
+ * all-reduced over NCCL); synchronises the context's stream before returning. */
+int smcpp_b200_copy_reduced_to_device(smcpp_b200_ctx *ctx, void *dst_device, int64_t count);
+
 /* Same E-step, but nothing is copied back to the host: results stay in the device buffers (per-contig
  * outputs and `reduced`).  Used to time the kernels alone; follow with smcpp_b200_fetch() for values. */
 int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E,
@@ -131,6 +135,11 @@ typedef struct smcpp_b200_stats_t {
     double fwd_max_mismatch, bwd_max_mismatch;
 } smcpp_b200_stats_t;
 int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out);
+
+/* Measured FP64 FMA throughput of this GPU (TFLOP/s, 2 flop per FMA): a register-resident DFMA loop on
+ * every SM, timed with CUDA events.  bench.py uses it as the compute roofline denominator (the driver's
+ * MEASURED_PEAKS.json holds HBM and bf16 figures only). */
+int smcpp_b200_fp64_peak(smcpp_b200_ctx *ctx, double *tflops);
 
 /* CUDA stream handle (cudaStream_t) the context launches on, for event timing by the caller. */
 int smcpp_b200_stream(smcpp_b200_ctx *ctx, void **stream);

@@ -1,7 +1,7 @@
 """SMCB1 bundles: a flat list of named little-endian arrays.
 
-Used to move inputs/outputs between pytest / bench.py and the oracle binaries under ``oracle/``
-(the C++ twin is ``oracle/ref_build/bundle_io.h``).  Format::
+A plain container used by pytest / bench.py to hand workloads to external checker binaries and read
+their dumps back (a C++ reader/writer of the same format ships with the test infrastructure).  Format::
 
     SMCB1\\n
     <name> <dtype> <ndim> <d0> ... <dN-1>\\n      dtype in {i4,i8,f4,f8,u1}

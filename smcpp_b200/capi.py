@@ -39,8 +39,8 @@ SYMBOLS = [
     "smcpp_b200_set_option", "smcpp_b200_set_contigs", "smcpp_b200_num_keys", "smcpp_b200_get_keys",
     "smcpp_b200_num_eig_keys", "smcpp_b200_get_eig_keys", "smcpp_b200_get_key_present", "smcpp_b200_total_blocks",
     "smcpp_b200_eigensystems", "smcpp_b200_host_eig", "smcpp_b200_host_eigensystems", "smcpp_b200_estep",
-    "smcpp_b200_reduced_device_ptr", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
-    "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat",
+    "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
+    "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat",
 ]
 
 
@@ -230,6 +230,10 @@ class Context:
         self._check(lib().smcpp_b200_reduced_device_ptr(self._h, ctypes.byref(p), ctypes.byref(n)), "reduced_device_ptr")
         return p.value, n.value
 
+    def copy_reduced_to_device(self, dst_ptr: int, count: int):
+        self._check(lib().smcpp_b200_copy_reduced_to_device(self._h, ctypes.c_void_p(dst_ptr), ctypes.c_int64(count)),
+                    "copy_reduced_to_device")
+
     def eigensystems(self, T, E) -> dict:
         return host_eigensystems(T, E, self.eig_keys)
 
@@ -237,6 +241,11 @@ class Context:
         s = Stats()
         self._check(lib().smcpp_b200_get_stats(self._h, ctypes.byref(s)), "get_stats")
         return s.as_dict()
+
+    def fp64_peak_tflops(self) -> float:
+        v = ctypes.c_double()
+        self._check(lib().smcpp_b200_fp64_peak(self._h, ctypes.byref(v)), "fp64_peak")
+        return v.value
 
     def stream(self) -> int:
         p = ctypes.c_void_p()

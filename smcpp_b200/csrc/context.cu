@@ -738,10 +738,44 @@ int smcpp_b200_reduced_device_ptr(smcpp_b200_ctx *ctx, void **ptr, int64_t *coun
     return 0;
 }
 
+int smcpp_b200_copy_reduced_to_device(smcpp_b200_ctx *ctx, void *dst_device, int64_t count)
+{
+    if (!ctx || !ctx->plan_valid || !dst_device) return 1;
+    const int64_t n = 1 + ctx->M + (int64_t)ctx->M * ctx->M + (int64_t)ctx->K * ctx->M;
+    if (count != n) return fail(ctx, "copy_reduced_to_device: count mismatch");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst_device, ctx->o_reduced.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
 int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out)
 {
     if (!ctx || !out) return 1;
     *out = ctx->stats;
+    return 0;
+}
+
+int smcpp_b200_fp64_peak(smcpp_b200_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return 1;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->w_counters.ensure(8));
+    double *sink = reinterpret_cast<double *>(ctx->w_counters.p);
+    const int iters = 1 << 14;
+    launch_fp64_peak(sink, 256, ctx->st);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(ctx->ev[5], ctx->st);
+        launch_fp64_peak(sink, iters, ctx->st);
+        cudaEventRecord(ctx->ev[6], ctx->st);
+        CU(cudaStreamSynchronize(ctx->st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+        const double flop = 2.0 * 8.0 * iters * 256.0 * 148.0 * 8.0;
+        best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
     return 0;
 }
 

@@ -94,28 +94,64 @@ void launch_setup(const Model &m, const double *pi_in, const double *T_in, const
 // ------------------------------------------------------------------------------------------------
 // Eigen 3.3.3 float sum() order (LinearVectorizedTraversal, SSE packets of 4, two accumulators), which
 // is what `alpha_hat.col(ell).sum()` compiles to in the reference (src/hmm.cpp:87).
-__device__ __forceinline__ float eigen_sum_f32(const float *v, int M)
+__device__ __forceinline__ float eigen_sum_f32(const float *v, int M, int astart)
 {
-    const int n4 = M >> 2, n8 = M >> 3;
+    // `astart` = leading coefficients before the first 16-byte aligned one of the reference's column:
+    // (4 - (ell*M) % 4) % 4 for column ell of the float matrix alpha_hat (0 whenever M % 4 == 0).
     float r;
-    if (n4) {
-        const float4 *v4 = reinterpret_cast<const float4 *>(v);
-        float4 p0 = v4[0];
-        if (n4 > 1) {
-            float4 p1 = v4[1];
-            for (int q = 1; q < n8; ++q) {
-                float4 a = v4[2 * q], b = v4[2 * q + 1];
-                p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
-                p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
+    if (astart == 0) {
+        const int n4 = M >> 2, n8 = M >> 3;
+        if (n4) {
+            const float4 *v4 = reinterpret_cast<const float4 *>(v);
+            float4 p0 = v4[0];
+            if (n4 > 1) {
+                float4 p1 = v4[1];
+                for (int q = 1; q < n8; ++q) {
+                    float4 a = v4[2 * q], b = v4[2 * q + 1];
+                    p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+                    p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
+                }
+                p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
+                if (n4 > 2 * n8) {
+                    float4 a = v4[2 * n8];
+                    p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+                }
             }
-            p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
-            if (n4 > 2 * n8) {
-                float4 a = v4[2 * n8];
-                p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+            r = __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
+            for (int i = n4 * 4; i < M; ++i) r = __fadd_rn(r, v[i]);
+        } else {
+            r = v[0];
+            for (int i = 1; i < M; ++i) r = __fadd_rn(r, v[i]);
+        }
+        return r;
+    }
+    if (astart > M) astart = M;
+    const int asize = ((M - astart) >> 2) << 2, asize2 = ((M - astart) >> 3) << 3;
+    const int aend = astart + asize, aend2 = astart + asize2;
+    if (asize) {
+        float p0[4], p1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p0[k] = v[astart + k];
+        if (asize > 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p1[k] = v[astart + 4 + k];
+            for (int i = astart + 8; i < aend2; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    p0[k] = __fadd_rn(p0[k], v[i + k]);
+                    p1[k] = __fadd_rn(p1[k], v[i + 4 + k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p0[k] = __fadd_rn(p0[k], p1[k]);
+            if (aend > aend2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p0[k] = __fadd_rn(p0[k], v[aend2 + k]);
             }
         }
-        r = __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
-        for (int i = n4 * 4; i < M; ++i) r = __fadd_rn(r, v[i]);
+        r = __fadd_rn(__fadd_rn(p0[0], p0[2]), __fadd_rn(p0[1], p0[3]));
+        for (int i = 0; i < astart; ++i) r = __fadd_rn(r, v[i]);
+        for (int i = aend; i < M; ++i) r = __fadd_rn(r, v[i]);
     } else {
         r = v[0];
         for (int i = 1; i < M; ++i) r = __fadd_rn(r, v[i]);
@@ -224,7 +260,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
 #pragma unroll
             for (int r = 0; r < R; ++r) xf[lane + 32 * r] = y[r];
             __syncwarp();
-            sf = eigen_sum_f32(xf, M);
+            sf = eigen_sum_f32(xf, M, (M & 3) ? (int)((4 - (((long)(b + 1) * M) & 3)) & 3) : 0);
             logc = log((double)sf);
 #pragma unroll
             for (int r = 0; r < R; ++r) x[r] = __fdiv_rn(y[r], sf);
@@ -818,5 +854,20 @@ void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int conti
 {
     k_gather_alpha<<<592, 256, 0, st>>>(m, p, w, contig, out);
 }
+
+// FP64 FMA peak probe: 8 independent chains per thread, 8 warps x 8 CTAs per SM
+__global__ void __launch_bounds__(256) k_fp64_peak(double *sink, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;
+}
+
+void launch_fp64_peak(double *sink, int iters, cudaStream_t st) { k_fp64_peak<<<148 * 8, 256, 0, st>>>(sink, iters); }
 
 }  // namespace smcb

@@ -102,5 +102,6 @@ void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
+void launch_fp64_peak(double *sink, int iters, cudaStream_t st);
 
 }  // namespace smcb

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's inference-manager interface for the E-step path.
+
+Names and meanings follow the reference's Cython class `_PyInferenceManager`
+(smcpp/_smcpp.pyx:97-308) and C++ `InferenceManager` (include/inference_manager.h:18-82):
+`E_step()`, `loglik()`, `xisums`, `gammas`, `gamma_sums`, `save_gamma`, plus the observation/hidden-state
+constructor arguments.  Everything numeric is done by libsmcpp_b200.so on the GPU through the C ABI
+(include/smcpp_b200.h); this class only owns buffers, shards contigs over GPUs and reshapes outputs.
+
+What is *not* here (out of the hot path): the CSFS and the autodiff'd M-step.  The inputs
+the reference derives from its model before the forward-backward -- pi, the transition matrix and the
+per-key emission vectors (do_dirty_work, src/inference_manager.cpp:213-229) -- are handed in with
+`set_hmm_inputs`.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import capi, parallel
+
+
+class InferenceManager:
+    """E-step engine over a list of contigs.
+
+    observations : list of int32 arrays [L, 1+3P]  (reference smcpp/_smcpp.pyx:133-151)
+    hidden_states: M+1 boundaries, first 0, last inf (reference include/inference_manager.h:41)
+    devices      : CUDA device indices of THIS process; contigs are sharded over them
+                   (one context per device, driven from one host thread each).
+    """
+
+    def __init__(self, observations, hidden_states, npop: int = 1, devices=(0,), keys=None):
+        self.hidden_states = np.asarray(hidden_states, np.float64)
+        self.M = len(self.hidden_states) - 1
+        self.npop = int(npop)
+        self._obs = [np.ascontiguousarray(o, np.int32) for o in observations]
+        for ob in self._obs:
+            if ob.ndim != 2 or ob.shape[1] != 1 + 3 * self.npop:
+                raise RuntimeError("observations must be int32 arrays of shape [L, 1 + 3*npop]")
+            if (ob[:, 0] <= 0).any():
+                raise RuntimeError("data are malformed: span <= 0")   # reference src/inference_manager.cpp:243-244
+        self.devices = list(devices)
+        self.keys = parallel.sort_keys(keys) if keys is not None else parallel.local_keys(self._obs)
+        self.K = self.keys.shape[0]
+        lengths = [o.shape[0] for o in self._obs]
+        self._shards = parallel.shard_contigs(lengths, len(self.devices))
+        self._ctx = []
+        for dev, idx in zip(self.devices, self._shards):
+            if not idx:
+                self._ctx.append(None)
+                continue
+            c = capi.Context(dev)
+            c.set_contigs([self._obs[i] for i in idx], self.npop, self.keys)
+            self._ctx.append(c)
+        live = [c for c in self._ctx if c is not None]
+        self.eig_keys = np.unique(np.concatenate([c.eig_keys for c in live])) if live else np.zeros(0, np.int32)
+        self.save_gamma = False
+        self._inputs = None
+        self._out = None
+
+    # -- inputs of the forward-backward (what do_dirty_work() leaves behind in the reference)
+    def set_hmm_inputs(self, pi, transition, emission_probs, eigensystems: dict | None = None):
+        pi = np.asarray(pi, np.float64)
+        T = np.asarray(transition, np.float64)
+        E = np.asarray(emission_probs, np.float64)
+        if pi.shape != (self.M,) or T.shape != (self.M, self.M) or E.shape != (self.K, self.M):
+            raise RuntimeError("set_hmm_inputs: expected pi[M], transition[M,M], emission_probs[K,M]")
+        self._inputs = (pi, T, E, eigensystems)
+
+    def set_option(self, name, value):
+        for c in self._ctx:
+            if c is not None:
+                c.set_option(name, value)
+
+    def _eig_for(self, ctx, T, E, eig):
+        """Eigensystems in the order of ctx.eig_keys (a shard may see a subset of the global eigen keys)."""
+        if eig is None:
+            return None
+        pos = {int(k): i for i, k in enumerate(eig["eig_key_idx"])}
+        sel = [pos[int(k)] for k in ctx.eig_keys]
+        return {k: np.ascontiguousarray(np.asarray(eig[k])[sel]) for k in ("eig_P", "eig_Pinv", "eig_d", "eig_dscaled", "eig_scale")}
+
+    def E_step(self, forward_backward_only: bool = False):
+        """Reference: _PyInferenceManager.E_step (smcpp/_smcpp.pyx:185-191) -> InferenceManager::Estep."""
+        if self._inputs is None:
+            raise RuntimeError("E_step: set_hmm_inputs() has not been called")
+        if self.save_gamma:
+            raise RuntimeError("save_gamma (full posterior decoding) is not part of this path yet")
+        pi, T, E, eig = self._inputs
+        results = [None] * len(self._ctx)
+        errors = []
+
+        def run(i, ctx):
+            try:
+                results[i] = ctx.estep(pi, T, E, self._eig_for(ctx, T, E, eig))
+            except Exception as ex:  # surfaced on the calling thread below
+                errors.append(ex)
+
+        threads = [threading.Thread(target=run, args=(i, c)) for i, c in enumerate(self._ctx) if c is not None]
+        if len(threads) == 1:
+            threads[0].run()
+        else:
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        if errors:
+            raise errors[0]
+        C = len(self._obs)
+        out = {"ll": np.zeros(C), "xisum": np.zeros((C, self.M, self.M)), "gamma0": np.zeros((C, self.M)),
+               "gamma_sums": np.zeros((C, self.K, self.M)), "key_present": np.zeros((C, self.K), np.uint8)}
+        red = np.zeros(1 + self.M + self.M * self.M + self.K * self.M)
+        for idx, r in zip(self._shards, results):
+            if r is None:
+                continue
+            for local, glob in enumerate(idx):
+                for k in ("ll", "xisum", "gamma0", "gamma_sums", "key_present"):
+                    out[k][glob] = r[k][local]
+            red += r["reduced"]
+        out["reduced"] = red
+        self._out = out
+
+    # -- outputs, shaped like the reference's Python properties
+    def _need(self):
+        if self._out is None:
+            raise RuntimeError("E_step() has not been run")
+        return self._out
+
+    def loglik(self) -> float:
+        """Reference: sum of InferenceManager::loglik() (smcpp/_smcpp.pyx:303-308)."""
+        return float(self._need()["ll"].sum())
+
+    @property
+    def logliks(self):
+        return self._need()["ll"].copy()
+
+    @property
+    def xisums(self):
+        """Reference: _PyInferenceManager.xisums (smcpp/_smcpp.pyx:257-263): one M x M matrix per contig."""
+        return [x.copy() for x in self._need()["xisum"]]
+
+    @property
+    def gammas(self):
+        """Reference: _PyInferenceManager.gammas (smcpp/_smcpp.pyx:233-239); without save_gamma only
+        column 0 is defined (src/hmm.cpp:150): returned as [M, 1] per contig."""
+        return [g.reshape(-1, 1).copy() for g in self._need()["gamma0"]]
+
+    @property
+    def gamma_sums(self):
+        """Reference: _PyInferenceManager.gamma_sums (smcpp/_smcpp.pyx:241-255): per contig a dict
+        {key tuple: vector[M]} holding exactly the keys present in that contig."""
+        o = self._need()
+        ret = []
+        for c in range(len(self._obs)):
+            ret.append({tuple(int(v) for v in self.keys[k]): o["gamma_sums"][c, k].copy()
+                        for k in range(self.K) if o["key_present"][c, k]})
+        return ret
+
+    @property
+    def reduced(self):
+        """[ll | gamma0 | xisum | gamma_sums] summed over contigs: the all-reduce payload."""
+        return self._need()["reduced"].copy()
+
+    def stats(self):
+        return [c.stats() if c is not None else None for c in self._ctx]
+
+    def close(self):
+        for c in self._ctx:
+            if c is not None:
+                c.close()
+        self._ctx = []

@@ -1,0 +1,199 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libsmcpp_b200.so), against
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  * the oracle port on fresh seeded inputs,
+  * the compiled reference itself where oracle/_ref travelled to this box,
+and, at BASELINE.json's full sizes, size-independent properties.
+
+Tolerances (helpers.py): log-likelihood 1e-8 relative (BASELINE.json north_star); xi / gamma statistics 1e-7
+of the largest entry.  Sequential mode (one chunk per contig) must reproduce the reference's
+float alpha_hat bit for bit.
+"""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_NAMES, LL_RTOL, STAT_RTOL, Golden, load_model, relmax
+from oracle import port, refrun
+from smcpp_b200 import capi, synth
+from smcpp_b200.inference import InferenceManager
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ctx(contigs, npop, ref, opts=None, lib_eig=False, keys=None):
+    ctx = capi.Context(0)
+    for k, v in (opts or {}).items():
+        ctx.set_option(k, v)
+    ctx.set_contigs(contigs, npop, keys)
+    out = ctx.estep(ref["pi"], ref["T"], ref["E"], None if lib_eig else ref)
+    return ctx, out
+
+
+def check_against(out, ref, ll_rtol=LL_RTOL, stat_rtol=STAT_RTOL):
+    assert abs(out["ll"].sum() - ref["ll"].sum()) <= ll_rtol * abs(ref["ll"].sum())
+    assert np.all(np.abs(out["ll"] - ref["ll"]) <= ll_rtol * np.abs(ref["ll"]))
+    for k in ("xisum", "gamma0", "gamma_sums"):
+        for c in range(len(ref["ll"])):
+            assert relmax(out[k][c], ref[k][c]) <= stat_rtol, (k, c)
+    assert np.array_equal(out["key_present"], ref["key_present"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden_sequential_bit_exact_forward(name):
+    g = Golden(name)
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"force_sequential": 1})
+    assert np.array_equal(ctx.keys, g.ref["keys"])
+    assert np.array_equal(ctx.eig_keys, g.ref["eig_key_idx"])
+    check_against(out, g.ref, ll_rtol=1e-13, stat_rtol=1e-11)
+    for c in range(len(g.contigs)):
+        assert np.array_equal(ctx.debug_alpha_hat(c), g.ref[f"alpha_hat_{c}"]), "float alpha_hat differs"
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("chunk,burn", [(64, 64), (128, 512), (37, 300)])
+def test_golden_chunked(name, chunk, burn):
+    g = Golden(name)
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": chunk, "burn_in_blocks": burn})
+    check_against(out, g.ref)
+    st = ctx.stats()
+    assert st["chunk_blocks"] <= chunk
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1_2k", "c2_1500", "m17_800", "m64_600", "ref_test_inference"])
+def test_golden_library_eigensystems(name):
+    g = Golden(name)
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, lib_eig=True)
+    check_against(out, g.ref)
+    ctx.close()
+
+
+def test_short_burn_in_is_repaired_by_sweeps():
+    # burn-in far too short: boundary checks must fail and the sweeps must restore the exact chain
+    g = Golden("c2_1500")
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": 50, "burn_in_blocks": 2})
+    st = ctx.stats()
+    assert st["fwd_redone"] > 0 and st["fwd_sweeps"] > 1
+    assert st["bwd_redone"] > 0 and st["bwd_sweeps"] > 1
+    check_against(out, g.ref)
+    # the context lengthens its burn-in for the next E-step
+    out2 = ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    assert ctx.stats()["burn_in_blocks"] > 2
+    check_against(out2, g.ref)
+    ctx.close()
+
+
+def test_zero_burn_in_degenerates_to_sequential_sweeps():
+    g = Golden("c1_2k")
+    ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0})
+    seq = port.hmm_estep(g.contigs[0][:400], g.ref)
+    assert abs(out["ll"][0] - seq["ll"]) <= 1e-12 * abs(seq["ll"])
+    assert relmax(out["xisum"][0], seq["xisum"]) < 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("M,n,L", [(16, 4, 3000), (32, 10, 2500), (8, 3, 1200), (33, 5, 700), (96, 8, 400), (128, 6, 300)])
+def test_fresh_inputs_against_port(M, n, L):
+    # fresh seeded inputs; pi / T / E come from a golden-independent recipe so no reference is needed on the box
+    rng = np.random.default_rng(M * 1000 + L)
+    w = synth.make_workload("fresh", 2, L, M, n, seed0=900 + M)
+    keys = np.unique(np.concatenate([c[:, 1:] for c in w.contigs]), axis=0)
+    K = keys.shape[0]
+    # a reversible-ish chain with the reference's uniform mixing, and emissions in (0, 1]
+    base = rng.random((M, M)) ** 4 + np.eye(M) * 50
+    T = base / base.sum(1, keepdims=True)
+    T = (1 - 1e-5) * T + 1e-5 / (M + 1)
+    pi = rng.random(M) + 0.1
+    pi /= pi.sum()
+    E = np.clip(rng.random((K, M)) * 0.9 + 0.05, 1e-3, 1.0)
+    eig_idx = np.array([k for k in range(K) if any(((c[:, 0] > 1) & (c[:, 1:] == keys[k]).all(1)).any() for c in w.contigs)], np.int32)
+    eig = capi.host_eigensystems(T, E, eig_idx)
+    if eig["eig_cplx"].any():
+        pytest.skip("random chain has complex eigenvalues")
+    ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
+    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512})
+    for c, obs in enumerate(w.contigs):
+        o = port.hmm_estep(obs, ref)
+        assert abs(out["ll"][c] - o["ll"]) <= LL_RTOL * abs(o["ll"])
+        for k in ("xisum", "gamma0", "gamma_sums"):
+            assert relmax(out[k][c], o[k]) <= STAT_RTOL, k
+    ctx.close()
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_harness did not travel to this box")
+@pytest.mark.parametrize("cfg,scale", [("C1", 1.0), ("C2", 0.05), ("C4", 0.05), ("C5-64", 0.01)])
+def test_baseline_configs_against_live_reference(cfg, scale):
+    w = synth.config(cfg, scale)
+    ref = refrun.run(w)
+    ctx, out = run_ctx(w.contigs, w.npop, ref)
+    check_against(out, ref)
+    ctx.close()
+
+
+def test_errors_follow_the_reference():
+    ctx = capi.Context(0)
+    bad = np.array([[1, -1, 0, 0], [0, 0, 0, 0]], np.int32)
+    with pytest.raises(RuntimeError, match="data are malformed: span <= 0"):
+        ctx.set_contigs([bad], 1)
+    ok = np.array([[1, -1, 0, 0], [5, 0, 0, 0], [1, 1, 0, 0]], np.int32)
+    with pytest.raises(RuntimeError, match="missing from the explicit key table"):
+        ctx.set_contigs([ok], 1, np.array([[-1, 0, 0], [0, 0, 0]], np.int32))
+    with pytest.raises(RuntimeError, match="set_contigs"):
+        ctx.estep(np.ones(4) / 4, np.eye(4), np.ones((1, 4)))
+    ctx.set_contigs([ok], 1)
+    with pytest.raises(ValueError):
+        ctx.estep(np.ones(4) / 4, np.eye(4), np.ones((2, 4)))     # K = 3
+    ctx.close()
+
+
+def test_explicit_global_key_table_and_sharding_sum():
+    # two shards with a shared key table must add up to the single-context result (the all-reduce contract)
+    g = Golden("ragged")
+    ctx, full = run_ctx(g.contigs, g.npop, g.ref)
+    im = InferenceManager(g.contigs, g.inp["hidden_states"], npop=g.npop, devices=[0, 0], keys=g.ref["keys"])
+    im.set_hmm_inputs(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    im.E_step()
+    assert np.allclose(im.reduced, full["reduced"], rtol=1e-12, atol=0)
+    assert im.loglik() == pytest.approx(g.ref["ll"].sum(), rel=1e-10)
+    gs = im.gamma_sums
+    for c in range(len(g.contigs)):
+        present = {tuple(int(v) for v in g.ref["keys"][k]) for k in range(g.ref["keys"].shape[0]) if g.ref["key_present"][c, k]}
+        assert set(gs[c].keys()) == present
+        assert relmax(im.xisums[c], g.ref["xisum"][c]) < STAT_RTOL
+    ctx.close()
+    im.close()
+
+
+def test_rerun_is_deterministic():
+    g = Golden("c4_twopop_1200")
+    ctx, a = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": 100})
+    b = ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    for k in ("ll", "xisum", "gamma0", "gamma_sums", "reduced"):
+        assert np.array_equal(a[k], b[k]), k
+    ctx.close()
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full size (1 x 10^6 blocks, M = 32): properties that need no reference run."""
+    w = synth.config("C2")
+    ref = load_model("C2")     # pi / T / E / eigensystems of this config, produced by the reference
+    keys = np.unique(w.contigs[0][:, 1:], axis=0)
+    assert np.array_equal(keys, ref["keys"])
+    ctx, out = run_ctx(w.contigs, 1, ref)
+    total_span = int(w.contigs[0][:, 0].astype(np.int64).sum())
+    # every block's posterior sums to its span (src/hmm.cpp:120-121, 135-136)
+    assert out["gamma_sums"].sum() == pytest.approx(total_span, rel=1e-9)
+    assert np.isfinite(out["ll"]).all() and out["ll"][0] < 0
+    assert (out["xisum"] >= 1e-20).all()
+    assert np.array_equal(out["reduced"][1 + 32 + 1024:].reshape(-1, 32), out["gamma_sums"][0])
+    # chunked == sequential (to the tolerance), at full size
+    ctx2, seq = run_ctx(w.contigs, 1, ref, {"force_sequential": 1})
+    assert abs(out["ll"][0] - seq["ll"][0]) <= 1e-10 * abs(seq["ll"][0])
+    assert relmax(out["xisum"][0], seq["xisum"][0]) <= 1e-8
+    assert relmax(out["gamma_sums"][0], seq["gamma_sums"][0]) <= 1e-8
+    # and the first 3000 blocks agree with the port run on that prefix through alpha_hat
+    a_gpu = ctx2.debug_alpha_hat(0)[:3001]
+    o = port.hmm_estep(w.contigs[0][:3000], ref, want_alpha=True)
+    assert np.array_equal(a_gpu, o["alpha_hat"])
+    ctx.close()
+    ctx2.close()

@@ -1,0 +1,48 @@
+"""Repository contract checks that need no GPU: the product never touches the oracle, the C ABI library
+loads and exports every symbol the header declares, and creating a context without a device fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from smcpp_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "smcpp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "oracle/" in txt or "libsmcb_oracle" in txt:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "smcpp_b200.h")).read()
+    declared = set(re.findall(r"\b(smcpp_b200_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"smcpp_b200_ctx", "smcpp_b200_stats_t"}
+    assert declared, "no declarations parsed"
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/smcpp_b200.h but not exported"
+    assert lib.smcpp_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        capi.Context(0)
+
+
+def test_built_for_sm100a():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
