@@ -683,23 +683,23 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
     const int smem = stats_smem_bytes(m);
-    switch (m.Mp / 32) {
-    case 1:
-        cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_stats<2><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
-        break;
-    case 2:
-        cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_stats<4><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
-        break;
-    case 3:
-        cudaFuncSetAttribute(k_stats<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_stats<6><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
-        break;
-    default:
-        cudaFuncSetAttribute(k_stats<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_stats<8><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w);
-        break;
+    // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
+    static int configured[5] = {0, 0, 0, 0, 0};
+    const int r = m.Mp / 32;
+    if (configured[r] < smem) {
+        switch (r) {
+        case 1: cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 2: cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        case 3: cudaFuncSetAttribute(k_stats<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        default: cudaFuncSetAttribute(k_stats<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        }
+        configured[r] = smem;
+    }
+    switch (r) {
+    case 1: k_stats<2><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w); break;
+    case 2: k_stats<4><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w); break;
+    case 3: k_stats<6><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w); break;
+    default: k_stats<8><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w); break;
     }
 }
 

@@ -85,7 +85,7 @@ def test_short_burn_in_is_repaired_by_sweeps():
 
 def test_zero_burn_in_degenerates_to_sequential_sweeps():
     g = Golden("c1_2k")
-    ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0})
+    ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0}, keys=g.ref["keys"])
     seq = port.hmm_estep(g.contigs[0][:400], g.ref)
     assert abs(out["ll"][0] - seq["ll"]) <= 1e-12 * abs(seq["ll"])
     assert relmax(out["xisum"][0], seq["xisum"]) < 1e-9
