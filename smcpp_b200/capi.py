@@ -183,7 +183,12 @@ class Context:
     def _eig_args(self, eig):
         if eig is None:
             return 0, None, None, None, None, None, []
-        keep = [np.ascontiguousarray(eig[k], np.float64) for k in ("eig_P", "eig_Pinv", "eig_d", "eig_dscaled", "eig_scale")]
+        sel = slice(None)
+        if "eig_key_idx" in eig:
+            # eigensystems are matched by key index: a context may hold a subset of the eigen keys
+            pos = {int(k): i for i, k in enumerate(np.asarray(eig["eig_key_idx"]))}
+            sel = [pos[int(k)] for k in self.eig_keys]
+        keep = [np.ascontiguousarray(np.asarray(eig[k], np.float64)[sel]) for k in ("eig_P", "eig_Pinv", "eig_d", "eig_dscaled", "eig_scale")]
         return (keep[0].shape[0], ptr(keep[0], c_f64p), ptr(keep[1], c_f64p), ptr(keep[2], c_f64p), ptr(keep[3], c_f64p),
                 ptr(keep[4], c_f64p), keep)
 

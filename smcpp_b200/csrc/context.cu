@@ -86,18 +86,21 @@ struct smcpp_b200_ctx {
     std::vector<int32_t> eig_of_key;  // K
     std::vector<uint8_t> present;     // C x K
     std::vector<int32_t> h_span;
-    std::vector<uint16_t> h_key;
+    std::vector<uint16_t> h_key;     // packed code: key id | (1 + eigen index) << 11 for span > 1 blocks
+    int hot_eig = -1;
     DevBuf<int32_t> d_span;
     DevBuf<uint16_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
     DevBuf<uint32_t> d_sl_mask;
+    DevBuf<int32_t> d_perm, d_seg;
     DevBuf<int> d_eig_of_key, d_key_of_eig;
 
     // ---- options
     int opt_chunk_blocks = 0;       // 0 = auto
     int opt_burn_in = 512;
-    int opt_target_warps = 148 * 16;
+    int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
+    int n_sm = 148;
     int opt_slab_blocks = 2048;
     double opt_fwd_tol = 4e-7, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
@@ -120,7 +123,7 @@ struct smcpp_b200_ctx {
     DevBuf<float> m_A32;
     DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
     DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
-        w_scratch, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
+        w_scratch, w_sums, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
     DevBuf<uint8_t> w_fwd_flag, w_bwd_flag;
     DevBuf<int> w_counters;
     PinBuf<int> h_counters;
@@ -132,7 +135,7 @@ struct smcpp_b200_ctx {
     Model model() const
     {
         Model m;
-        m.M = M; m.Mp = Mp; m.K = K; m.n_eig = n_eig;
+        m.M = M; m.Mp = Mp; m.K = K; m.n_eig = n_eig; m.hot_eig = hot_eig;
         m.pi = m_pi.p; m.Td = m_Td.p; m.TdT = m_TdT.p; m.A32 = m_A32.p; m.E = m_E.p;
         m.eig_of_key = d_eig_of_key.p; m.key_of_eig = d_key_of_eig.p;
         m.P = m_P.p; m.PT = m_PT.p; m.Pinv = m_Pinv.p; m.PinvT = m_PinvT.p;
@@ -145,10 +148,11 @@ struct smcpp_b200_ctx {
         p.n_contigs = C; p.n_chunks = n_chunks; p.n_slabs = n_slabs;
         p.chunk_blocks = plan_Lc; p.burn_in = plan_burn; p.slab_blocks = plan_slab;
         p.total_blocks = total;
-        p.span = d_span.p; p.key = d_key.p;
+        p.span = d_span.p; p.kcode = d_key.p;
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
         p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
         p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
+        p.perm = d_perm.p; p.seg = d_seg.p;
         return p;
     }
     Work work() const
@@ -159,7 +163,7 @@ struct smcpp_b200_ctx {
         w.ll_chunk = w_ll_chunk.p; w.bstart_used = w_bstart_used.p; w.beta_out = w_beta_out.p;
         w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p;
         w.counters = w_counters.p;
-        w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p;
+        w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p; w.sums = w_sums.p;
         w.ll = o_ll.p; w.xisum = o_xisum.p; w.gamma0 = o_gamma0.p; w.gamma_sums = o_gamma_sums.p; w.reduced = o_reduced.p;
         return w;
     }
@@ -207,6 +211,10 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device)
         delete ctx;
         return 1;
     }
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) ctx->n_sm = prop.multiProcessorCount;
+    }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&ctx->ev_setup_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_bwd_done, cudaEventDisableTiming);
@@ -223,7 +231,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
+    ctx->d_sl_mask.release(); ctx->d_perm.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
@@ -231,7 +239,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->w_alpha.release(); ctx->w_cnorm.release(); ctx->w_start_used.release(); ctx->w_end_alpha.release();
     ctx->w_end_alpha_prev.release(); ctx->w_bvec.release(); ctx->w_ll_chunk.release(); ctx->w_bstart_used.release();
     ctx->w_beta_out.release(); ctx->w_beta_out_prev.release(); ctx->w_Xpart.release(); ctx->w_Rpart.release();
-    ctx->w_dpart.release(); ctx->w_gspart.release(); ctx->w_scratch.release(); ctx->o_ll.release();
+    ctx->w_dpart.release(); ctx->w_gspart.release(); ctx->w_scratch.release(); ctx->w_sums.release(); ctx->o_ll.release();
     ctx->o_xisum.release(); ctx->o_gamma0.release(); ctx->o_gamma_sums.release(); ctx->o_reduced.release();
     ctx->w_fwd_flag.release(); ctx->w_bwd_flag.release(); ctx->w_counters.release(); ctx->h_counters.release();
     ctx->h_out.release();
@@ -251,7 +259,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     std::string n(name);
     if (n == "chunk_blocks") ctx->opt_chunk_blocks = (int)value;
     else if (n == "burn_in_blocks") { ctx->opt_burn_in = (int)value; ctx->burn_in_adapt = 0; }
-    else if (n == "target_warps") ctx->opt_target_warps = std::max(1, (int)value);
+    else if (n == "target_warps") ctx->opt_target_warps = std::max(0, (int)value);
     else if (n == "slab_blocks") ctx->opt_slab_blocks = std::max(32, (int)value);
     else if (n == "fwd_tol") ctx->opt_fwd_tol = value;
     else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
@@ -314,7 +322,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
             return std::lexicographical_compare(a.v.begin(), a.v.begin() + Q, b.v.begin(), b.v.begin() + Q);
         });
     }
-    if (table.size() >= 65535) return fail(ctx, "set_contigs: more than 65534 distinct observation keys");
+    if (table.size() > 2047) return fail(ctx, "set_contigs: more than 2047 distinct observation keys");
     const int K = (int)table.size();
     ctx->K = K;
     ctx->keys.assign((size_t)K * Q, 0);
@@ -344,6 +352,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     ctx->h_span.resize(ctx->total);
     ctx->h_key.resize(ctx->total);
     ctx->present.assign((size_t)n_contigs * K, 0);
+    std::vector<int64_t> eig_count(std::max(1, ctx->n_eig), 0);
     for (int c = 0; c < n_contigs; ++c) {
         const int32_t *o = obs[c];
         KeyRow last{};
@@ -358,10 +367,15 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
                 last = kr;
             }
             ctx->h_span[g0 + l] = row[0];
-            ctx->h_key[g0 + l] = (uint16_t)last_id;
+            const int e = row[0] > 1 ? ctx->eig_of_key[last_id] : -1;
+            ctx->h_key[g0 + l] = (uint16_t)(last_id | ((e + 1) << 11));
+            if (e >= 0) ++eig_count[e];
             ctx->present[(size_t)c * K + last_id] = 1;
         }
     }
+    ctx->hot_eig = -1;
+    for (int e = 0; e < ctx->n_eig; ++e)
+        if (ctx->hot_eig < 0 || eig_count[e] > eig_count[ctx->hot_eig]) ctx->hot_eig = e;
     CU(ctx->d_span.ensure(ctx->total));
     CU(ctx->d_key.ensure(ctx->total));
     CU(cudaMemcpy(ctx->d_span.p, ctx->h_span.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -414,8 +428,22 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     if (ctx->opt_force_sequential) Lc = (int)maxL;
     else if (ctx->opt_chunk_blocks > 0) Lc = ctx->opt_chunk_blocks;
     else {
-        int64_t per = (ctx->total + ctx->opt_target_warps - 1) / ctx->opt_target_warps;
-        Lc = (int)std::max<int64_t>(per, std::max(burn, 64));
+        // as many chunks as fit in ONE resident wave of the recursion kernels (a partial second wave would
+        // double the time), but never shorter than the burn-in, which bounds the redundant work by 2x
+        int target = ctx->opt_target_warps;
+        if (target <= 0) target = Mp == 32 ? resident_warps32(ctx->n_sm) : ctx->n_sm * 16;
+        auto chunks_for = [&](int64_t lc) {
+            int64_t n = 0;
+            for (int c = 0; c < ctx->C; ++c) n += (ctx->blk_off[c + 1] - ctx->blk_off[c] + lc - 1) / lc;
+            return n;
+        };
+        int64_t lo = std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
+        if (chunks_for(lo) <= target) hi = lo;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (chunks_for(mid) <= target) hi = mid; else lo = mid + 1;
+        }
+        Lc = (int)hi;
     }
     if (Lc > maxL) Lc = (int)maxL;
     if (Lc < 1) Lc = 1;
@@ -430,6 +458,9 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     ctx->col_off.assign(C, 0);
     std::vector<int32_t> ch_contig, ch_start, ch_len, sl_contig, sl_start, sl_len;
     std::vector<uint32_t> sl_mask;
+    std::vector<int32_t> perm(ctx->total), seg;
+    std::vector<uint64_t> sortbuf;
+    const int NEp = ctx->n_eig;
     int64_t cols = 0;
     for (int c = 0; c < C; ++c) {
         const int64_t L = ctx->blk_off[c + 1] - ctx->blk_off[c];
@@ -448,13 +479,29 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             uint32_t mask = 0;
             const int64_t g0 = ctx->blk_off[c] + s0;
             for (int b = 0; b < n; ++b) {
-                if (ctx->h_span[g0 + b] == 1) mask |= 1u;
-                else mask |= 2u << ctx->eig_of_key[ctx->h_key[g0 + b]];
+                const int code = ctx->h_key[g0 + b] >> 11;
+                mask |= code == 0 ? 1u : (2u << (code - 1));
             }
             sl_contig.push_back(c);
             sl_start.push_back(s0);
             sl_len.push_back(n);
             sl_mask.push_back(mask);
+            // processing order of the statistics kernel: span-1 blocks sorted by key, then each eigen key's blocks
+            sortbuf.clear();
+            for (int b = 0; b < n; ++b) {
+                const uint16_t kc = ctx->h_key[g0 + b];
+                const uint64_t cls = kc >> 11;   // 0 = span 1, 1 + e otherwise
+                const uint64_t key = cls == 0 ? (kc & 2047) : 0;
+                sortbuf.push_back((cls << 48) | (key << 32) | (uint32_t)(s0 + b));
+            }
+            std::sort(sortbuf.begin(), sortbuf.end());
+            size_t at = 0;
+            for (int cls = 0; cls <= NEp; ++cls) {
+                seg.push_back((int32_t)at);
+                while (at < sortbuf.size() && (int)(sortbuf[at] >> 48) == cls) ++at;
+            }
+            seg.push_back((int32_t)at);
+            for (int b = 0; b < n; ++b) perm[g0 + b] = (int32_t)(sortbuf[b] & 0xffffffffu);
         }
         ctx->slab_off[c + 1] = (int)sl_contig.size();
     }
@@ -478,18 +525,20 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     UP(d_sl_start, sl_start);
     UP(d_sl_len, sl_len);
     UP(d_sl_mask, sl_mask);
+    UP(d_perm, perm);
+    UP(d_seg, seg);
 #undef UP
     const int K = ctx->K, NE = std::max(1, ctx->n_eig);
     const size_t MM = (size_t)Mp * Mp;
     CU(ctx->m_pi.ensure(Mp));
-    CU(ctx->m_Td.ensure((size_t)M * Mp));
-    CU(ctx->m_TdT.ensure((size_t)M * Mp));
+    CU(ctx->m_Td.ensure((size_t)Mp * Mp));
+    CU(ctx->m_TdT.ensure((size_t)Mp * Mp));
     CU(ctx->m_E.ensure((size_t)K * Mp));
-    CU(ctx->m_A32.ensure((size_t)K * M * Mp));
-    CU(ctx->m_P.ensure((size_t)NE * M * Mp));
-    CU(ctx->m_PT.ensure((size_t)NE * M * Mp));
-    CU(ctx->m_Pinv.ensure((size_t)NE * M * Mp));
-    CU(ctx->m_PinvT.ensure((size_t)NE * M * Mp));
+    CU(ctx->m_A32.ensure((size_t)K * Mp * Mp));
+    CU(ctx->m_P.ensure((size_t)NE * Mp * Mp));
+    CU(ctx->m_PT.ensure((size_t)NE * Mp * Mp));
+    CU(ctx->m_Pinv.ensure((size_t)NE * Mp * Mp));
+    CU(ctx->m_PinvT.ensure((size_t)NE * Mp * Mp));
     CU(ctx->m_dsc.ensure((size_t)NE * Mp));
     CU(ctx->m_logd.ensure((size_t)NE * Mp));
     CU(ctx->m_dr.ensure((size_t)NE * Mp));
@@ -513,7 +562,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->w_Rpart.ensure((size_t)ctx->n_slabs * NE * MM));
     CU(ctx->w_dpart.ensure((size_t)ctx->n_slabs * NE * Mp));
     CU(ctx->w_gspart.ensure((size_t)ctx->n_slabs * K * Mp));
-    CU(ctx->w_scratch.ensure((size_t)C * 3 * MM));
+    CU(ctx->w_scratch.ensure((size_t)C * 2 * MM));
+    CU(ctx->w_sums.ensure((size_t)C * (MM + (size_t)ctx->n_eig * MM + (size_t)ctx->n_eig * Mp + (size_t)K * Mp)));
     CU(ctx->o_ll.ensure(C));
     CU(ctx->o_xisum.ensure((size_t)C * M * M));
     CU(ctx->o_gamma0.ensure((size_t)C * M));
@@ -629,7 +679,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     cudaEventRecord(ctx->ev[3], ctx->st);
     launch_finalize(m, p, w, ctx->st);
     cudaEventRecord(ctx->ev[4], ctx->st);
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 4;
     CU(cudaGetLastError());
     ctx->stats.n_chunks = p.n_chunks;
     ctx->stats.chunk_blocks = p.chunk_blocks;

@@ -1,5 +1,6 @@
 // smcpp_b200 -- CUDA kernels of the E-step (sm_100a).  See estep_kernels.cuh / DESIGN.md.
 #include "estep_kernels.cuh"
+#include "device_utils.cuh"
 
 #include <math.h>
 
@@ -7,22 +8,6 @@ namespace smcb {
 
 constexpr int kSeqWarps = 4;     // warps (= chunks) per CTA in the recursion kernels
 constexpr int kStatThreads = 256;
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// d^span for integer span >= 1 through the precomputed log|d| (the reference calls std::pow,
-// src/hmm.cpp:75; the relative difference is <= |span log d| * 2^-53).
-__device__ __forceinline__ double pow_span(double d, double logd, int span)
-{
-    if (d == 0.0) return 0.0;
-    double r = exp((double)span * logd);
-    return (d < 0.0 && (span & 1)) ? -r : r;
-}
 
 // ------------------------------------------------------------------------------------------------
 // setup: padded / transposed operand tables
@@ -36,33 +21,35 @@ __global__ void k_setup(Model m, const double *pi_in, const double *T_in, const 
     double *E = const_cast<double *>(m.E);
     float *A32 = const_cast<float *>(m.A32);
     for (long x = tid; x < Mp; x += nth) pi[x] = x < M ? pi_in[x] : 0.0;
-    for (long x = tid; x < (long)M * Mp; x += nth) {
+    for (long x = tid; x < (long)Mp * Mp; x += nth) {
         int i = (int)(x / Mp), j = (int)(x % Mp);
-        Td[x] = j < M ? T_in[(long)i * M + j] : 0.0;      // Td(i,j)
-        TdT[x] = j < M ? T_in[(long)j * M + i] : 0.0;     // row i of TdT holds Td(.,i): TdT[i*Mp + j] = Td(j,i)
+        const bool in = i < M && j < M;
+        Td[x] = in ? T_in[(long)i * M + j] : 0.0;      // Td(i,j)
+        TdT[x] = in ? T_in[(long)j * M + i] : 0.0;     // row i of TdT holds Td(.,i): TdT[i*Mp + j] = Td(j,i)
     }
     for (long x = tid; x < (long)K * Mp; x += nth) {
         int k = (int)(x / Mp), j = (int)(x % Mp);
         E[x] = j < M ? E_in[(long)k * M + j] : 0.0;
     }
-    for (long x = tid; x < (long)K * M * Mp; x += nth) {
+    for (long x = tid; x < (long)K * Mp * Mp; x += nth) {
         int j = (int)(x % Mp);
         long ki = x / Mp;
-        int i = (int)(ki % M), k = (int)(ki / M);
+        int i = (int)(ki % Mp), k = (int)(ki / Mp);
         // (diag(e_k) Td^T)(j,i) = e_k(j) Td(i,j) in double, then rounded to float: reference src/hmm.cpp:85-86
-        A32[x] = j < M ? (float)(E_in[(long)k * M + j] * T_in[(long)i * M + j]) : 0.0f;
+        A32[x] = (i < M && j < M) ? (float)(E_in[(long)k * M + j] * T_in[(long)i * M + j]) : 0.0f;
     }
     double *P = const_cast<double *>(m.P), *PT = const_cast<double *>(m.PT), *Pinv = const_cast<double *>(m.Pinv),
            *PinvT = const_cast<double *>(m.PinvT);
-    for (long x = tid; x < (long)NE * M * Mp; x += nth) {
+    for (long x = tid; x < (long)NE * Mp * Mp; x += nth) {
         int c = (int)(x % Mp);
         long er = x / Mp;
-        int r = (int)(er % M), e = (int)(er / M);
+        int r = (int)(er % Mp), e = (int)(er / Mp);
         const double *Pe = P_in + (long)e * M * M, *Pie = Pinv_in + (long)e * M * M;
-        P[x] = c < M ? Pe[(long)r * M + c] : 0.0;        // P(r,c)
-        PT[x] = c < M ? Pe[(long)c * M + r] : 0.0;       // PT[(e*M+a)*Mp + j] = P(j,a)
-        Pinv[x] = c < M ? Pie[(long)r * M + c] : 0.0;    // Pinv(r,c)
-        PinvT[x] = c < M ? Pie[(long)c * M + r] : 0.0;   // PinvT[(e*M+i)*Mp + a] = Pinv(a,i)
+        const bool in = r < M && c < M;
+        P[x] = in ? Pe[(long)r * M + c] : 0.0;        // P(r,c)
+        PT[x] = in ? Pe[(long)c * M + r] : 0.0;       // PT[(e*Mp+a)*Mp + j] = P(j,a)
+        Pinv[x] = in ? Pie[(long)r * M + c] : 0.0;    // Pinv(r,c)
+        PinvT[x] = in ? Pie[(long)c * M + r] : 0.0;   // PinvT[(e*Mp+i)*Mp + a] = Pinv(a,i)
     }
     double *dsc = const_cast<double *>(m.dsc), *logd = const_cast<double *>(m.logd), *dr = const_cast<double *>(m.dr);
     for (long x = tid; x < (long)NE * Mp; x += nth) {
@@ -82,7 +69,7 @@ __global__ void k_setup(Model m, const double *pi_in, const double *T_in, const 
 void launch_setup(const Model &m, const double *pi_in, const double *T_in, const double *E_in, const double *P_in,
                   const double *Pinv_in, const double *d_in, const double *dsc_in, const double *scale_in, cudaStream_t st)
 {
-    long work = (long)m.K * m.M * m.Mp;
+    long work = (long)m.K * m.Mp * m.Mp;
     int blocks = (int)((work + 255) / 256);
     if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
@@ -92,73 +79,6 @@ void launch_setup(const Model &m, const double *pi_in, const double *T_in, const
 // ------------------------------------------------------------------------------------------------
 // forward recursion: one warp per chunk, lane owns states j = lane + 32 r
 // ------------------------------------------------------------------------------------------------
-// Eigen 3.3.3 float sum() order (LinearVectorizedTraversal, SSE packets of 4, two accumulators), which
-// is what `alpha_hat.col(ell).sum()` compiles to in the reference (src/hmm.cpp:87).
-__device__ __forceinline__ float eigen_sum_f32(const float *v, int M, int astart)
-{
-    // `astart` = leading coefficients before the first 16-byte aligned one of the reference's column:
-    // (4 - (ell*M) % 4) % 4 for column ell of the float matrix alpha_hat (0 whenever M % 4 == 0).
-    float r;
-    if (astart == 0) {
-        const int n4 = M >> 2, n8 = M >> 3;
-        if (n4) {
-            const float4 *v4 = reinterpret_cast<const float4 *>(v);
-            float4 p0 = v4[0];
-            if (n4 > 1) {
-                float4 p1 = v4[1];
-                for (int q = 1; q < n8; ++q) {
-                    float4 a = v4[2 * q], b = v4[2 * q + 1];
-                    p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
-                    p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
-                }
-                p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
-                if (n4 > 2 * n8) {
-                    float4 a = v4[2 * n8];
-                    p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
-                }
-            }
-            r = __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
-            for (int i = n4 * 4; i < M; ++i) r = __fadd_rn(r, v[i]);
-        } else {
-            r = v[0];
-            for (int i = 1; i < M; ++i) r = __fadd_rn(r, v[i]);
-        }
-        return r;
-    }
-    if (astart > M) astart = M;
-    const int asize = ((M - astart) >> 2) << 2, asize2 = ((M - astart) >> 3) << 3;
-    const int aend = astart + asize, aend2 = astart + asize2;
-    if (asize) {
-        float p0[4], p1[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p0[k] = v[astart + k];
-        if (asize > 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p1[k] = v[astart + 4 + k];
-            for (int i = astart + 8; i < aend2; i += 8) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    p0[k] = __fadd_rn(p0[k], v[i + k]);
-                    p1[k] = __fadd_rn(p1[k], v[i + 4 + k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p0[k] = __fadd_rn(p0[k], p1[k]);
-            if (aend > aend2) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) p0[k] = __fadd_rn(p0[k], v[aend2 + k]);
-            }
-        }
-        r = __fadd_rn(__fadd_rn(p0[0], p0[2]), __fadd_rn(p0[1], p0[3]));
-        for (int i = 0; i < astart; ++i) r = __fadd_rn(r, v[i]);
-        for (int i = aend; i < M; ++i) r = __fadd_rn(r, v[i]);
-    } else {
-        r = v[0];
-        for (int i = 1; i < M; ++i) r = __fadd_rn(r, v[i]);
-    }
-    return r;
-}
-
 template <int R>
 __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Work w, int pass)
 {
@@ -199,8 +119,8 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
     const int bend = s + len;
     for (int b = b0; b < bend; ++b) {
         const int span = p.span[g0 + b];
-        const int k = p.key[g0 + b];
-        const int e = span > 1 ? m.eig_of_key[k] : -1;
+        const int kc = p.kcode[g0 + b];
+        const int k = kc & 2047, e = (kc >> 11) - 1;
         double logc;
         float sf = 0.f;
         if (e >= 0) {
@@ -212,7 +132,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
             double u[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) u[r] = 0.0;
-            const double *PinvT = m.PinvT + (size_t)e * M * Mp;
+            const double *PinvT = m.PinvT + (size_t)e * Mp * Mp;
             for (int i = 0; i < M; ++i) {
                 const double xi = xd[i];
 #pragma unroll
@@ -228,7 +148,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
             double a[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) a[r] = 0.0;
-            const double *PT = m.PT + (size_t)e * M * Mp;
+            const double *PT = m.PT + (size_t)e * Mp * Mp;
             for (int i = 0; i < M; ++i) {
                 const double gi = xd[i];
 #pragma unroll
@@ -250,7 +170,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
             float y[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) y[r] = 0.f;
-            const float *A = m.A32 + (size_t)k * M * Mp;
+            const float *A = m.A32 + (size_t)k * Mp * Mp;
             for (int i = 0; i < M; ++i) {
                 const float xi = xf[i];
 #pragma unroll
@@ -289,6 +209,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
 
 void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
 {
+    if (m.Mp == 32) { launch_forward32(m, p, w, pass, st); return; }
     const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
     const size_t smem = (size_t)kSeqWarps * m.Mp * (sizeof(double) + sizeof(float));
     switch (m.Mp / 32) {
@@ -361,8 +282,8 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
         }
         const bool storing = b < bend;
         const int span = p.span[g0 + b];
-        const int k = p.key[g0 + b];
-        const int e = span > 1 ? m.eig_of_key[k] : -1;
+        const int kc = p.kcode[g0 + b];
+        const int k = kc & 2047, e = (kc >> 11) - 1;
         double *bv = w.bvec + (size_t)(g0 + b) * Mp;
         double nb[R];
 #pragma unroll
@@ -376,7 +297,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
             double wv[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) wv[r] = 0.0;
-            const double *P = m.P + (size_t)e * M * Mp;
+            const double *P = m.P + (size_t)e * Mp * Mp;
             for (int i = 0; i < M; ++i) {
                 const double bi = xd[i];
 #pragma unroll
@@ -393,7 +314,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
                 xd[j] = pow_span(m.dsc[(size_t)e * Mp + j], m.logd[(size_t)e * Mp + j], span) * wv[r];
             }
             __syncwarp();
-            const double *Pinv = m.Pinv + (size_t)e * M * Mp;
+            const double *Pinv = m.Pinv + (size_t)e * Mp * Mp;
             for (int a = 0; a < M; ++a) {
                 const double ga = xd[a];
 #pragma unroll
@@ -432,6 +353,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
 
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
 {
+    if (m.Mp == 32) { launch_backward32(m, p, w, pass, st); return; }
     const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
     const size_t smem = (size_t)kSeqWarps * m.Mp * sizeof(double);
     switch (m.Mp / 32) {
@@ -534,9 +456,9 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
             for (int bq = warp; bq < NB; bq += NW) {
                 const int b = s0 + tile0 + bq;
                 int valid = 0, k = 0;
-                if (tile0 + bq < n && p.span[g0 + b] == 1) {
+                if (tile0 + bq < n && (p.kcode[g0 + b] >> 11) == 0) {
                     valid = 1;
-                    k = p.key[g0 + b];
+                    k = p.kcode[g0 + b] & 2047;
                     const float *ap = alpha_col(b), *ac = ap + Mp;
                     const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
                     double be[R], acur[R], part = 0.0;
@@ -596,7 +518,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 #pragma unroll
             for (int j = 0; j < TM; ++j) acc[i][j] = 0.0;
         double dacc = 0.0;
-        const double *PinvT = m.PinvT + (size_t)e * M * Mp;
+        const double *PinvT = m.PinvT + (size_t)e * Mp * Mp;
         const double sc = m.scale[e];
         for (int tile0 = 0; tile0 < n; tile0 += NB) {
             for (int bq = warp; bq < NB; bq += NW) {
@@ -604,7 +526,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
                 int valid = 0;
                 if (tile0 + bq < n) {
                     const int span = p.span[g0 + b];
-                    if (span > 1 && m.eig_of_key[p.key[g0 + b]] == e) {
+                    if ((p.kcode[g0 + b] >> 11) == e + 1) {
                         valid = 1;
                         const float *ap = alpha_col(b);
                         const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
@@ -682,6 +604,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
+    if (m.Mp == 32) { launch_stats32(m, p, w, st); return; }
     const int smem = stats_smem_bytes(m);
     // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
     static int configured[5] = {0, 0, 0, 0, 0};
@@ -704,15 +627,47 @@ void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------
-// finalize: one CTA per contig
+// finalize: (1) slab partials -> per-contig sums, fully parallel; (2) one CTA per contig maps the eigenbasis
+// accumulators back to state space and applies the closing steps of reference src/hmm.cpp:150-152
 // ------------------------------------------------------------------------------------------------
+size_t sums_stride(const Model &m)
+{
+    const size_t MM = (size_t)m.Mp * m.Mp;
+    return MM + (size_t)m.n_eig * MM + (size_t)m.n_eig * m.Mp + (size_t)m.K * m.Mp;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w)
+{
+    const int Mp = m.Mp, K = m.K, NE = m.n_eig;
+    const size_t MM = (size_t)Mp * Mp;
+    const size_t oR = MM, oD = oR + (size_t)NE * MM, oG = oD + (size_t)NE * Mp, stride = oG + (size_t)K * Mp;
+    const int t = blockIdx.y;
+    const size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (x >= stride) return;
+    const int sl0 = p.slab_off[t], sl1 = p.slab_off[t + 1];
+    const double *src;
+    size_t sstride;
+    uint32_t bit;
+    if (x < oR) { src = w.Xpart + x; sstride = MM; bit = 1u; }
+    else if (x < oD) { const size_t y = x - oR; src = w.Rpart + y; sstride = (size_t)NE * MM; bit = 2u << (int)(y / MM); }
+    else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 2u << (int)(y / Mp); }
+    else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 1u; }
+    double acc = 0.0;
+    for (int s = sl0; s < sl1; ++s)
+        if (p.sl_mask[s] & bit) acc += src[(size_t)s * sstride];
+    w.sums[(size_t)t * stride + x] = acc;
+}
+
 __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
 {
     const int M = m.M, Mp = m.Mp, K = m.K, NE = m.n_eig;
     const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     const int sl0 = p.slab_off[t], sl1 = p.slab_off[t + 1];
     const size_t MM = (size_t)Mp * Mp;
-    double *X = w.scratch + (size_t)t * 3 * MM, *A = X + MM, *G = A + MM;
+    const size_t oR = MM, oD = oR + (size_t)NE * MM, oG = oD + (size_t)NE * Mp, stride = oG + (size_t)K * Mp;
+    double *S = w.sums + (size_t)t * stride;
+    double *X = S;                                     // accumulates in place
+    double *A = w.scratch + (size_t)t * 2 * MM, *G = A + MM;
     __shared__ uint32_t cmask;
     if (tid == 0) {
         uint32_t mk = 0;
@@ -721,42 +676,23 @@ __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
     }
     __syncthreads();
     const uint32_t mask = cmask;
-    // X = sum of the span-1 partials
-    for (size_t x = tid; x < MM; x += nth) {
-        double acc = 0.0;
-        for (int s = sl0; s < sl1; ++s)
-            if (p.sl_mask[s] & 1u) acc += w.Xpart[(size_t)s * MM + x];
-        X[x] = acc;
-    }
-    // gamma_sums = sum of the span-1 partials (unpadded output [K][M])
     double *gso = w.gamma_sums + (size_t)t * K * M;
     for (int x = tid; x < K * M; x += nth) {
         const int k = x / M, j = x % M;
-        double acc = 0.0;
-        for (int s = sl0; s < sl1; ++s)
-            if (p.sl_mask[s] & 1u) acc += w.gspart[((size_t)s * K + k) * Mp + j];
-        gso[x] = acc;
+        gso[x] = S[oG + (size_t)k * Mp + j];
     }
     __syncthreads();
     for (int e = 0; e < NE; ++e) {
         if (!(mask & (2u << e))) continue;
         const double *dsc = m.dsc + (size_t)e * Mp, *dr = m.dr + (size_t)e * Mp;
-        const double *P = m.P + (size_t)e * M * Mp, *Pinv = m.Pinv + (size_t)e * M * Mp;
+        const double *P = m.P + (size_t)e * Mp * Mp, *Pinv = m.Pinv + (size_t)e * Mp * Mp;
+        const double *R = S + oR + (size_t)e * MM, *D = S + oD + (size_t)e * Mp;
         const int ke = m.key_of_eig[e];
         // Acc(a,b) = R(a,b) / (d~_a - d~_b), Acc(a,a) = D(a)
         for (size_t x = tid; x < MM; x += nth) {
             const int a = (int)(x / Mp), b = (int)(x % Mp);
             double acc = 0.0;
-            if (a < M && b < M) {
-                if (a == b) {
-                    for (int s = sl0; s < sl1; ++s)
-                        if (p.sl_mask[s] & (2u << e)) acc += w.dpart[((size_t)s * NE + e) * Mp + a];
-                } else {
-                    for (int s = sl0; s < sl1; ++s)
-                        if (p.sl_mask[s] & (2u << e)) acc += w.Rpart[((size_t)s * NE + e) * MM + x];
-                    acc /= dsc[a] - dsc[b];
-                }
-            }
+            if (a < M && b < M) acc = a == b ? D[a] : R[x] / (dsc[a] - dsc[b]);
             A[x] = acc;
         }
         __syncthreads();
@@ -826,6 +762,8 @@ __global__ void k_reduce(Model m, Plan p, Work w)
 
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
+    const size_t stride = sums_stride(m);
+    k_reduce_partials<<<dim3((unsigned)((stride + 255) / 256), p.n_contigs), 256, 0, st>>>(m, p, w);
     k_finalize<<<p.n_contigs, 256, 0, st>>>(m, p, w);
     const long n = 1 + m.M + (long)m.M * m.M + (long)m.K * m.M;
     k_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(m, p, w);

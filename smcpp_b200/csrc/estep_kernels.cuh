@@ -21,17 +21,18 @@ constexpr int kMaxEig = 30;       // eigen keys representable in a slab type mas
 // (lane) dimension; pads are zero.
 struct Model {
     int M, Mp, K, n_eig;
+    int hot_eig;             // eigen index with the most span>1 blocks (kept in registers by the M<=32 kernels), or -1
     const double *pi;        // [Mp]
-    const double *Td;        // [M][Mp]   Td[i*Mp + j] = Td(i,j)
-    const double *TdT;       // [M][Mp]   TdT[j*Mp + i] = Td(i,j)
-    const float *A32;        // [K][M][Mp] A32[(k*M + i)*Mp + j] = fl32(e_k(j) * Td(i,j))
+    const double *Td;        // [Mp][Mp]  Td[i*Mp + j] = Td(i,j)   (all tables: Mp rows, zero padded)
+    const double *TdT;       // [Mp][Mp]  TdT[j*Mp + i] = Td(i,j)
+    const float *A32;        // [K][Mp][Mp] A32[(k*Mp + i)*Mp + j] = fl32(e_k(j) * Td(i,j))
     const double *E;         // [K][Mp]
     const int *eig_of_key;   // [K]  -1 or eigen index
     const int *key_of_eig;   // [n_eig]
-    const double *P;         // [n_eig][M][Mp]  P[(e*M + i)*Mp + a] = P_r(i,a)
-    const double *PT;        // [n_eig][M][Mp]  PT[(e*M + a)*Mp + j] = P_r(j,a)
-    const double *Pinv;      // [n_eig][M][Mp]  Pinv[(e*M + a)*Mp + i] = Pinv_r(a,i)
-    const double *PinvT;     // [n_eig][M][Mp]  PinvT[(e*M + i)*Mp + a] = Pinv_r(a,i)
+    const double *P;         // [n_eig][Mp][Mp]  P[(e*Mp + i)*Mp + a] = P_r(i,a)
+    const double *PT;        // [n_eig][Mp][Mp]  PT[(e*Mp + a)*Mp + j] = P_r(j,a)
+    const double *Pinv;      // [n_eig][Mp][Mp]  Pinv[(e*Mp + a)*Mp + i] = Pinv_r(a,i)
+    const double *PinvT;     // [n_eig][Mp][Mp]  PinvT[(e*Mp + i)*Mp + a] = Pinv_r(a,i)
     const double *dsc;       // [n_eig][Mp] d_r / scale
     const double *logd;      // [n_eig][Mp] log|dsc|
     const double *dr;        // [n_eig][Mp] d_r
@@ -46,7 +47,7 @@ struct Plan {
     int64_t total_blocks;
     // per block (concatenated over contigs)
     const int32_t *span;     // [total]
-    const uint16_t *key;     // [total]
+    const uint16_t *kcode;   // [total]  bits 0-10: key id; bits 11-15: 1 + eigen index if span > 1, else 0
     // per contig
     const int64_t *blk_off;  // [C+1] first global block of contig
     const int64_t *col_off;  // [C]   first alpha column of contig (chunk c at col_off + c*(chunk_blocks+1))
@@ -61,6 +62,9 @@ struct Plan {
     const int32_t *sl_start; // [n_slabs]
     const int32_t *sl_len;   // [n_slabs]
     const uint32_t *sl_mask; // [n_slabs] bit0: has span-1 blocks; bit 1+e: has span>1 blocks of eigen key e
+    // processing order of the statistics kernel: per slab [span-1 blocks sorted by key | eigen key 0 | eigen key 1 ...]
+    const int32_t *perm;     // [total]  block index within the contig, stored at the slab's own offset
+    const int32_t *seg;      // [n_slabs][n_eig + 2] segment boundaries (relative to the slab start)
 };
 
 // Work buffers.
@@ -82,7 +86,8 @@ struct Work {
     double *Rpart;           // [n_slabs][n_eig][Mp*Mp]
     double *dpart;           // [n_slabs][n_eig][Mp]
     double *gspart;          // [n_slabs][K][Mp]
-    double *scratch;         // [C][3][Mp*Mp]
+    double *scratch;         // [C][2][Mp*Mp]  temporaries of k_finalize
+    double *sums;            // [C][sum_stride] slab partials reduced per contig: X | R_e | D_e | gs
     // outputs (device)
     double *ll;              // [C]
     double *xisum;           // [C][M][M]
@@ -95,6 +100,11 @@ struct Work {
 void launch_setup(const Model &m, const double *pi_in, const double *T_in, const double *E_in, const double *P_in,
                   const double *Pinv_in, const double *d_in, const double *dsc_in, const double *scale_in, cudaStream_t st);
 void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
+void launch_forward32(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);   // Mp == 32
+void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);  // Mp == 32
+size_t sums_stride(const Model &m);
+int resident_warps32(int n_sm);
+void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);

@@ -1,0 +1,333 @@
+// smcpp_b200 -- sufficient statistics for M <= 32 on the FP64 tensor path (mma.sync.m8n8k4.f64, SASS DMMA).
+//
+// The per-block rank-1 updates of the E-step are GEMMs over the block index:
+//   span-1 blocks:  X    += A_prev B^T          A_prev = [alpha_{l-1}],  B = [beta_l o e_k / (c_l p_l)]
+//   span>1 blocks:  U     = Pinv_r A_prev       (one GEMM, blocks in the n dimension)
+//                   R_e  += (U o pw) Y^T - U Z^T  Y = [C_l w_l], Z = Y o pw     (blocks in the k dimension)
+// k_stats32 walks a slab's blocks in a precomputed order (plan-time permutation: span-1 blocks sorted by key,
+// then the span>1 blocks of each eigen key), so every pass is dense -- no masking -- and the per-key gamma
+// sums are accumulated in registers over key runs.  One warp owns a 32x32 FP64 accumulator in DMMA C-fragment
+// layout; the 8 warps of a CTA reduce through shared memory in fixed order (bitwise reproducible).
+//
+// Fragment layout of mma.m8n8k4 (lane = 4*r + q, r = lane/4, q = lane%4):
+//   A (8x4, row): a = A[r][q]        B (4x8, col): b = B[q][r]        C (8x8): c0 = C[r][2q], c1 = C[r][2q+1]
+#include "device_utils.cuh"
+#include "estep_kernels.cuh"
+
+namespace smcb {
+
+constexpr int kS32Warps = 8;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// sum over the 8 lanes that share q (= over r)
+__device__ __forceinline__ double sum_over_r(double v)
+{
+    v += __shfl_xor_sync(kFullMask, v, 4);
+    v += __shfl_xor_sync(kFullMask, v, 8);
+    v += __shfl_xor_sync(kFullMask, v, 16);
+    return v;
+}
+// sum over the 4 lanes that share r (= over q)
+__device__ __forceinline__ double sum_over_q(double v)
+{
+    v += __shfl_xor_sync(kFullMask, v, 1);
+    v += __shfl_xor_sync(kFullMask, v, 2);
+    return v;
+}
+
+// accumulator tile -> shared [32][33] (padded), element (row 8mt + r, col 8nt + 2q + h)
+__device__ __forceinline__ void store_acc(double *sm, const double (&acc)[4][4][2], int r, int q)
+{
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            sm[(8 * mt + r) * 33 + 8 * nt + 2 * q] = acc[mt][nt][0];
+            sm[(8 * mt + r) * 33 + 8 * nt + 2 * q + 1] = acc[mt][nt][1];
+        }
+}
+
+__global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Work w)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = m.K, NE = m.n_eig;
+    const int slab = blockIdx.x;
+    const int t = p.sl_contig[slab], s0 = p.sl_start[slab];
+    const uint32_t mask = p.sl_mask[slab];
+    const int64_t g0 = p.blk_off[t];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int32_t *perm = p.perm + g0 + s0;                 // this slab's processing order (block index in contig)
+    const int32_t *seg = p.seg + (size_t)slab * (NE + 2);   // [dense | eig 0 | eig 1 | ... ] offsets into perm
+
+    double *tiles = reinterpret_cast<double *>(smem_raw);                   // [kS32Warps][32*33]
+    double *gs = tiles + (size_t)kS32Warps * 32 * 33;                       // [K][32]
+    double *bnd = gs + (size_t)K * 32;                                      // [kS32Warps][2][32] boundary key sums
+    double *dred = bnd + (size_t)kS32Warps * 2 * 32;                        // [kS32Warps][32]
+    int *bkey = reinterpret_cast<int *>(dred + (size_t)kS32Warps * 32);     // [kS32Warps][2]
+
+    const int Lc = p.chunk_blocks;
+    const int64_t colbase = p.col_off[t];
+    auto alpha_col = [&](int b) -> const float * {   // alpha_hat column "before block b" (the one after it is + 32)
+        const int cb = b / Lc;
+        return w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (b - cb * Lc)) * 32;
+    };
+
+    // ================= span-1 blocks: X and the per-key gamma sums =================
+    if (mask & 1u) {
+        for (int x = tid; x < K * 32; x += kS32Warps * 32) gs[x] = 0.0;
+        if (lane < 2) bkey[warp * 2 + lane] = -1;
+        __syncthreads();
+        const int d0 = seg[0], d1 = seg[1];
+        const int ngrp = (d1 - d0 + 3) >> 2;
+        const int gbeg = (int)((long)ngrp * warp / kS32Warps), gend = (int)((long)ngrp * (warp + 1) / kS32Warps);
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        double gacc[4] = {0.0, 0.0, 0.0, 0.0};   // gamma sum of the current key run, states 8nt + r, partial over q
+        int cur = -1;
+        bool first_open = true;                   // the first key of this warp's range may be shared with the previous warp
+        auto flush = [&](int key) {
+            if (key < 0) return;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const double v = sum_over_q(gacc[nt]);
+                if (q == 0) {
+                    if (first_open) bnd[(warp * 2 + 0) * 32 + 8 * nt + r] = v;       // boundary slot: combined in warp order below
+                    else gs[(size_t)key * 32 + 8 * nt + r] += v;                      // interior key: this warp is its only writer ... so far
+                }
+                gacc[nt] = 0.0;
+            }
+            if (first_open) {
+                if (lane == 0) bkey[warp * 2 + 0] = key;
+                first_open = false;
+            }
+        };
+        for (int g = gbeg; g < gend; ++g) {
+            const int pos = d0 + 4 * g + q;
+            const bool valid = pos < d1;
+            const int b = valid ? perm[pos] : 0;
+            const int64_t gb = g0 + b;
+            const int k = valid ? (p.kcode[gb] & 2047) : -1;
+            double av[4], bvv[4], vv[4], be[4], ac[4], ek[4];
+            double pp = 0.0, cn = 1.0;
+            if (valid) {
+                const float *ap = alpha_col(b);
+                const double *bv = w.bvec + (size_t)gb * 32;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    av[i] = (double)ap[8 * i + r];
+                    ac[i] = (double)ap[32 + 8 * i + r];
+                    be[i] = bv[8 * i + r];
+                    ek[i] = __ldg(m.E + (size_t)k * 32 + 8 * i + r);
+                }
+                cn = (double)w.cnorm[gb];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { av[i] = 0.0; ac[i] = 0.0; be[i] = 0.0; ek[i] = 0.0; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pp = fma(ac[i], be[i], pp);
+            pp = sum_over_r(pp);                                      // p = alpha_l . beta_l   (all lanes take part)
+            const double inv_p = valid ? 1.0 / pp : 0.0;
+            const double inv_cp = inv_p / cn;                         // 1 / (c_l p_l)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bvv[i] = be[i] * ek[i] * inv_cp;
+                vv[i] = ac[i] * be[i] * inv_p;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bvv[nt]);
+            // gamma sums by key run (the list is key-sorted, so runs are long)
+            const int k0 = __shfl_sync(kFullMask, k, 0), k1 = __shfl_sync(kFullMask, k, 1), k2 = __shfl_sync(kFullMask, k, 2),
+                      k3 = __shfl_sync(kFullMask, k, 3);
+            if (k0 == cur && k1 == cur && k2 == cur && k3 == cur) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
+            } else {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int kq = qq == 0 ? k0 : qq == 1 ? k1 : qq == 2 ? k2 : k3;
+                    if (kq < 0) continue;
+                    if (kq != cur) { flush(cur); cur = kq; }
+                    if (q == qq) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
+                    }
+                }
+            }
+        }
+        // the last key of the range may be shared with the next warp: boundary slot 1 (slot 0 if it is also the first)
+        if (cur >= 0) {
+            if (first_open) flush(cur);
+            else {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double v = sum_over_q(gacc[nt]);
+                    if (q == 0) bnd[(warp * 2 + 1) * 32 + 8 * nt + r] = v;
+                }
+                if (lane == 0) bkey[warp * 2 + 1] = cur;
+            }
+        }
+        store_acc(tiles + (size_t)warp * 32 * 33, acc, r, q);
+        __syncthreads();
+        // fixed-order combination: X tiles, then the boundary key sums in warp order
+        double *Xp = w.Xpart + (size_t)slab * 1024;
+        for (int x = tid; x < 1024; x += kS32Warps * 32) {
+            const int i = x >> 5, j = x & 31;
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < kS32Warps; ++ww) s += tiles[(size_t)ww * 32 * 33 + i * 33 + j];
+            Xp[x] = s;
+        }
+        if (tid < 32) {
+            for (int ww = 0; ww < kS32Warps; ++ww)
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int key = bkey[ww * 2 + sl];
+                    if (key >= 0) gs[(size_t)key * 32 + tid] += bnd[(ww * 2 + sl) * 32 + tid];
+                }
+        }
+        __syncthreads();
+        double *gp = w.gspart + (size_t)slab * K * 32;
+        for (int x = tid; x < K * 32; x += kS32Warps * 32) gp[x] = gs[x];
+        __syncthreads();
+    }
+
+    // ================= span>1 blocks, one pass per eigen key present in the slab =================
+    for (int e = 0; e < NE; ++e) {
+        if (!(mask & (2u << e))) continue;
+        const int l0 = seg[1 + e], l1 = seg[2 + e];
+        const int ngrp = (l1 - l0 + 7) >> 3;
+        const int gbeg = (int)((long)ngrp * warp / kS32Warps), gend = (int)((long)ngrp * (warp + 1) / kS32Warps);
+        // Pinv_r as A fragments: A[a = 8mt + r][i = 4kt + q]
+        double pinv_f[4][8];
+        {
+            const double *Pinv = m.Pinv + (size_t)e * 1024;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int kt = 0; kt < 8; ++kt) pinv_f[mt][kt] = Pinv[(8 * mt + r) * 32 + 4 * kt + q];
+        }
+        double dsc[4], logd[4], invd[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            dsc[mt] = m.dsc[e * 32 + 8 * mt + r];
+            logd[mt] = m.logd[e * 32 + 8 * mt + r];
+            invd[mt] = dsc[mt] != 0.0 ? 1.0 / dsc[mt] : 0.0;
+        }
+        const double sc = m.scale[e];
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int g = gbeg; g < gend; ++g) {
+            const int base = l0 + 8 * g;
+            // U = Pinv_r [alpha_prev of 8 blocks]: B[i = 4kt + q][block r]
+            double u[4][2];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) u[mt][0] = u[mt][1] = 0.0;
+            {
+                const bool vr = base + r < l1;
+                const int br = vr ? perm[base + r] : 0;
+                const float *ap = alpha_col(br);
+#pragma unroll
+                for (int kt = 0; kt < 8; ++kt) {
+                    const double bfr = vr ? (double)ap[4 * kt + q] : 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) dmma884(u[mt][0], u[mt][1], pinv_f[mt][kt], bfr);
+                }
+            }
+            // per lane: blocks 2q + h, states 8mt + r
+            double xs[4][2], ys[4][2], zs[4][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool vb = base + 2 * q + h < l1;
+                const int b = vb ? perm[base + 2 * q + h] : 0;
+                const int64_t gb = g0 + b;
+                const int span = vb ? p.span[gb] : 2;
+                const double *bv = w.bvec + (size_t)gb * 32;
+                double wv[4], pw[4], dot = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    wv[mt] = vb ? bv[8 * mt + r] : 0.0;
+                    pw[mt] = pow_span(dsc[mt], logd[mt], span);
+                    dot = fma(pw[mt] * u[mt][h], wv[mt], dot);
+                }
+                dot = sum_over_r(dot);
+                const double C = vb ? 1.0 / (sc * dot) : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const double y = C * wv[mt];
+                    xs[mt][h] = u[mt][h] * pw[mt];
+                    ys[mt][h] = y;
+                    zs[mt][h] = y * pw[mt];
+                    dacc[mt] = fma(y * u[mt][h] * (double)span, pw[mt] * invd[mt], dacc[mt]);
+                }
+            }
+            // R += X Y^T - U Z^T over the 8 blocks (two k-tiles: blocks {2q} and {2q+1})
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(acc[mt][nt][0], acc[mt][nt][1], xs[mt][h], ys[nt][h]);
+                        dmma884(acc[mt][nt][0], acc[mt][nt][1], -u[mt][h], zs[nt][h]);
+                    }
+        }
+        store_acc(tiles + (size_t)warp * 32 * 33, acc, r, q);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const double v = sum_over_q(dacc[mt]);
+            if (q == 0) dred[warp * 32 + 8 * mt + r] = v;
+        }
+        __syncthreads();
+        double *Rp = w.Rpart + ((size_t)slab * NE + e) * 1024;
+        for (int x = tid; x < 1024; x += kS32Warps * 32) {
+            const int i = x >> 5, j = x & 31;
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < kS32Warps; ++ww) s += tiles[(size_t)ww * 32 * 33 + i * 33 + j];
+            Rp[x] = s;
+        }
+        if (tid < 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < kS32Warps; ++ww) s += dred[ww * 32 + tid];
+            w.dpart[((size_t)slab * NE + e) * 32 + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+size_t stats32_smem_bytes(const Model &m)
+{
+    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32) * sizeof(double) +
+           (size_t)kS32Warps * 2 * sizeof(int);
+}
+
+void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+{
+    const size_t smem = stats32_smem_bytes(m);
+    static size_t configured = 0;
+    if (configured < smem) {
+        cudaFuncSetAttribute(k_stats32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w);
+}
+
+}  // namespace smcb

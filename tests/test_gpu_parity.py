@@ -87,8 +87,11 @@ def test_zero_burn_in_degenerates_to_sequential_sweeps():
     g = Golden("c1_2k")
     ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0}, keys=g.ref["keys"])
     seq = port.hmm_estep(g.contigs[0][:400], g.ref)
-    assert abs(out["ll"][0] - seq["ll"]) <= 1e-12 * abs(seq["ll"])
-    assert relmax(out["xisum"][0], seq["xisum"]) < 1e-9
+    st = ctx.stats()
+    assert st["fwd_sweeps"] > 1 and st["bwd_sweeps"] > 1      # every boundary starts wrong and is repaired
+    # sweeps stop once every boundary agrees to the float noise floor (fwd_tol), not bit for bit
+    assert abs(out["ll"][0] - seq["ll"]) <= LL_RTOL * abs(seq["ll"])
+    assert relmax(out["xisum"][0], seq["xisum"]) <= STAT_RTOL
     ctx.close()
 
 
