@@ -27,7 +27,8 @@ class Stats(ctypes.Structure):
                 ("bwd_redone", ctypes.c_int32), ("kernel_launches", ctypes.c_int32),
                 ("ms_setup", ctypes.c_float), ("ms_forward", ctypes.c_float), ("ms_backward", ctypes.c_float),
                 ("ms_stats", ctypes.c_float), ("ms_finalize", ctypes.c_float), ("ms_total", ctypes.c_float),
-                ("fwd_max_mismatch", ctypes.c_double), ("bwd_max_mismatch", ctypes.c_double)]
+                ("fwd_max_mismatch", ctypes.c_double), ("bwd_max_mismatch", ctypes.c_double),
+                ("mma_rounds", ctypes.c_int32), ("mma_steps", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

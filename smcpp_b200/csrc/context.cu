@@ -79,6 +79,7 @@ struct smcpp_b200_ctx {
 
     // ---- dataset (set_contigs)
     int C = 0, npop = 0, K = 0, n_eig = 0;
+    bool contigs_ok = false;
     int64_t total = 0;
     std::vector<int64_t> blk_off;
     std::vector<int32_t> keys;        // K x 3P
@@ -105,6 +106,7 @@ struct smcpp_b200_ctx {
     double opt_fwd_tol = 4e-7, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
     int opt_force_sequential = 0;
+    int opt_mma_min_chunks = 64;    // use the 8-chunks-per-warp tensor-path recursions from this many chunks on
     int burn_in_adapt = 0;          // grows when boundary checks fail (sticky between E-steps)
 
     // ---- plan
@@ -120,7 +122,9 @@ struct smcpp_b200_ctx {
     DevBuf<double> d_in;            // staged raw inputs
     PinBuf<double> h_in;
     DevBuf<double> m_pi, m_Td, m_TdT, m_E, m_P, m_PT, m_Pinv, m_PinvT, m_dsc, m_logd, m_dr, m_scale, m_logscale;
-    DevBuf<float> m_A32;
+    DevBuf<float> m_A32, m_A32q;
+    DevBuf<double> m_F_Td, m_F_P, m_F_PT, m_F_Pinv, m_F_PinvT, m_Eq, m_dscq, m_logdq;
+    bool use_mma = false;
     DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
     DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
         w_scratch, w_sums, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
@@ -140,6 +144,8 @@ struct smcpp_b200_ctx {
         m.eig_of_key = d_eig_of_key.p; m.key_of_eig = d_key_of_eig.p;
         m.P = m_P.p; m.PT = m_PT.p; m.Pinv = m_Pinv.p; m.PinvT = m_PinvT.p;
         m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
+        m.F_Td = m_F_Td.p; m.F_P = m_F_P.p; m.F_PT = m_F_PT.p; m.F_Pinv = m_F_Pinv.p; m.F_PinvT = m_F_PinvT.p;
+        m.Eq = m_Eq.p; m.dscq = m_dscq.p; m.logdq = m_logdq.p; m.A32q = m_A32q.p;
         return m;
     }
     Plan plan() const
@@ -235,7 +241,9 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
-    ctx->m_dr.release(); ctx->m_scale.release(); ctx->m_logscale.release(); ctx->m_A32.release();
+    ctx->m_dr.release(); ctx->m_scale.release(); ctx->m_logscale.release(); ctx->m_A32.release(); ctx->m_A32q.release();
+    ctx->m_F_Td.release(); ctx->m_F_P.release(); ctx->m_F_PT.release(); ctx->m_F_Pinv.release(); ctx->m_F_PinvT.release();
+    ctx->m_Eq.release(); ctx->m_dscq.release(); ctx->m_logdq.release();
     ctx->w_alpha.release(); ctx->w_cnorm.release(); ctx->w_start_used.release(); ctx->w_end_alpha.release();
     ctx->w_end_alpha_prev.release(); ctx->w_bvec.release(); ctx->w_ll_chunk.release(); ctx->w_bstart_used.release();
     ctx->w_beta_out.release(); ctx->w_beta_out_prev.release(); ctx->w_Xpart.release(); ctx->w_Rpart.release();
@@ -265,6 +273,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
     else if (n == "max_sweeps") ctx->opt_max_sweeps = std::max(1, (int)value);
     else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
+    else if (n == "mma_min_chunks") ctx->opt_mma_min_chunks = std::max(1, (int)value);
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;
@@ -277,6 +286,8 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     if (n_contigs <= 0 || !obs || !lengths) return fail(ctx, "set_contigs: no contigs");
     if (npop < 1 || npop > 2) return fail(ctx, "set_contigs: npop must be 1 or 2");
     CU(cudaSetDevice(ctx->device));
+    ctx->contigs_ok = false;
+    ctx->plan_valid = false;
     const int W = 1 + 3 * npop, Q = 3 * npop;
     ctx->C = n_contigs;
     ctx->npop = npop;
@@ -389,6 +400,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
         CU(cudaMemcpy(ctx->d_key_of_eig.p, ctx->eig_keys.data(), ctx->n_eig * sizeof(int), cudaMemcpyHostToDevice));
     ctx->plan_valid = false;
     ctx->M = 0;
+    ctx->contigs_ok = true;
     return 0;
 }
 
@@ -431,7 +443,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         // as many chunks as fit in ONE resident wave of the recursion kernels (a partial second wave would
         // double the time), but never shorter than the burn-in, which bounds the redundant work by 2x
         int target = ctx->opt_target_warps;
-        if (target <= 0) target = Mp == 32 ? resident_warps32(ctx->n_sm) : ctx->n_sm * 16;
+        if (target <= 0) target = Mp == 32 ? std::min(resident_warps32m(ctx->n_sm), ctx->n_sm * 8) * 8 : ctx->n_sm * 16;
         auto chunks_for = [&](int64_t lc) {
             int64_t n = 0;
             for (int c = 0; c < ctx->C; ++c) n += (ctx->blk_off[c + 1] - ctx->blk_off[c] + lc - 1) / lc;
@@ -544,6 +556,17 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->m_dr.ensure((size_t)NE * Mp));
     CU(ctx->m_scale.ensure(NE));
     CU(ctx->m_logscale.ensure(NE));
+    if (Mp == 32) {
+        CU(ctx->m_A32q.ensure((size_t)K * 1024));
+        CU(ctx->m_F_Td.ensure(1024));
+        CU(ctx->m_F_P.ensure((size_t)NE * 1024));
+        CU(ctx->m_F_PT.ensure((size_t)NE * 1024));
+        CU(ctx->m_F_Pinv.ensure((size_t)NE * 1024));
+        CU(ctx->m_F_PinvT.ensure((size_t)NE * 1024));
+        CU(ctx->m_Eq.ensure((size_t)K * 32));
+        CU(ctx->m_dscq.ensure((size_t)NE * 32));
+        CU(ctx->m_logdq.ensure((size_t)NE * 32));
+    }
     CU(ctx->w_alpha.ensure((size_t)cols * Mp));
     CU(ctx->w_cnorm.ensure(ctx->total));
     CU(ctx->w_bvec.ensure((size_t)ctx->total * Mp));
@@ -582,7 +605,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
                      const double *P, const double *Pinv, const double *d, const double *dsc, const double *scale,
                      bool upload)
 {
-    if (ctx->C == 0) return fail(ctx, "estep: set_contigs() has not been called");
+    if (ctx->C == 0 || !ctx->contigs_ok) return fail(ctx, "estep: set_contigs() has not been called (or failed)");
     if (M < 1 || M > kMaxMp) return fail(ctx, "estep: M must be in [1, 128]");
     CU(cudaSetDevice(ctx->device));
     if (make_plan(ctx, M)) return 1;
@@ -618,6 +641,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         const double *di = ctx->d_in.p;
         launch_setup(ctx->model(), di + o_pi, di + o_T, di + o_E, di + o_P, di + o_Pi, di + o_d, di + o_ds, di + o_sc, ctx->st);
         ctx->stats.kernel_launches = 1;
+        if (ctx->Mp == 32) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 2; }
     } else {
         cudaEventRecord(ctx->ev[0], ctx->st);
         ctx->stats.kernel_launches = 0;
@@ -630,10 +654,12 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     cudaEventRecord(ctx->ev_setup_done, ctx->st);
     // backward recursion runs concurrently on the second stream (it does not depend on alpha)
     CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
-    launch_backward(m, p, w, 0, ctx->st2);
+    const bool mma = m.Mp == 32 && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
+    ctx->use_mma = mma;
+    if (mma) launch_backward32m(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
     launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st2);
     // forward recursion
-    launch_forward(m, p, w, 0, ctx->st);
+    if (mma) launch_forward32m(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
     launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
     ctx->stats.kernel_launches += 4;
     cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
@@ -647,6 +673,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         float f;
         std::memcpy(&f, &ctx->h_counters.p[2], 4); fwd_mm = std::max(fwd_mm, f);
         std::memcpy(&f, &ctx->h_counters.p[3], 4); bwd_mm = std::max(bwd_mm, f);
+        if (ctx->h_counters.p[4] > 0) { ctx->stats.mma_rounds = ctx->h_counters.p[4]; ctx->stats.mma_steps = ctx->h_counters.p[5]; }
         if (nf == 0 && nb == 0) break;
         if (fwd_sweeps + bwd_sweeps > ctx->opt_max_sweeps) break;
         CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));

@@ -38,6 +38,17 @@ struct Model {
     const double *dr;        // [n_eig][Mp] d_r
     const double *scale;     // [n_eig]
     const double *logscale;  // [n_eig]
+    // tensor-path (Mp == 32) operand tables, see recursion32_mma.cu: matrices in mma B-fragment order,
+    // vectors and the float step matrices permuted to the per-lane state order st(q, idx)
+    const double *F_Td;      // [1024]
+    const double *F_P;       // [n_eig][1024]  W = P_r
+    const double *F_PT;      // [n_eig][1024]  W = P_r^T
+    const double *F_Pinv;    // [n_eig][1024]  W = Pinv_r
+    const double *F_PinvT;   // [n_eig][1024]  W = Pinv_r^T
+    const double *Eq;        // [K][32]
+    const double *dscq;      // [n_eig][32]
+    const double *logdq;     // [n_eig][32]
+    const float *A32q;       // [K][32][4][8]
 };
 
 // Static per-dataset layout (set_contigs) + per-plan chunking.
@@ -105,6 +116,10 @@ void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, c
 size_t sums_stride(const Model &m);
 int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
+void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
+void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp == 32, pass 0, <= 8 chunks / warp
+void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);
+int resident_warps32m(int n_sm);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);

@@ -1,0 +1,456 @@
+// smcpp_b200 -- forward / backward recursions for M <= 32 on the FP64 tensor path, 8 chunks per warp.
+//
+// A GEMV of the recursion (y = W x, 32x32 double) for EIGHT independent chunks at once is one small GEMM,
+// Y[8 chunks][32] = X[8][32] W^T, i.e. 32 mma.sync.m8n8k4.f64 (SASS: DMMA) per warp instead of 8 x 32 DFMA + 8 x 16
+// broadcast loads: the chunk index is the m dimension, the operand matrix W sits in shared memory in
+// B-fragment order (one LDS.64 per DMMA, shared by every warp of the CTA) and the 8 chunks give the
+// instruction-level parallelism that one dependent chain per warp cannot (profiles/r1b: the one-chunk-per-warp
+// kernels issue 10-30 % of the time).
+//
+// Lane = 4n + q: n = chunk slot (row of A and C fragments), q = k-slot.  A lane holds, for its chunk, the 8 states
+//     st(q, idx) = 8 (idx / 2) + 2 q + (idx % 2),   idx = 0..7
+// which is exactly where mma puts C[n][8 nt + 2q + h] (idx = 2 nt + h).  Feeding those registers back as
+// A-fragment k-tile idx works because the k index of an MMA may be permuted freely as long as A and B agree: the
+// B fragments are built (k_setup_frags) for the state order st(q, idx).  So chained GEMVs need no shuffles.
+//
+// The 8 chunks of a warp advance in lockstep "rounds": every round has one block type (span-1, or span>1 with
+// eigen key e) -- the type of the first unfinished chunk -- and only chunks whose current block has that type
+// commit.  With the alternating run/site structure of real and synthetic contigs all 8 commit every round;
+// arbitrary data only loses efficiency, never correctness.
+//
+// Numerics: same reference semantics as recursion32.cu (float alpha_hat, fl32 step matrix, sequential axpy
+// order and Eigen's sum() order for the float normaliser, 1e-10f floor); the fp64 normalisation multiplies by
+// 1/sum instead of dividing and sums the 32 doubles in a different order (a 1e-16 relative effect; the
+// one-chunk kernels, used for the sequential mode and for repair sweeps, keep the reference's exact order).
+#include "device_utils.cuh"
+#include "estep_kernels.cuh"
+
+namespace smcb {
+
+constexpr int kMW = 4;             // warps per CTA
+constexpr unsigned kAll = 0xffffffffu;
+
+__device__ __forceinline__ int st_of(int q, int idx) { return 8 * (idx >> 1) + 2 * q + (idx & 1); }
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// y[chunk][.] = W x[chunk][.] for the 8 chunks of the warp; F = W in B-fragment order (shared or global)
+template <bool kShared>
+__device__ __forceinline__ void gemv8(const double *F, const double (&v)[8], double (&y)[8], int lane)
+{
+    double c[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) c[nt][0] = c[nt][1] = 0.0;
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const double b = kShared ? F[(kt * 4 + nt) * 32 + lane] : __ldg(F + (kt * 4 + nt) * 32 + lane);
+            dmma(c[nt][0], c[nt][1], v[kt], b);
+        }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { y[2 * nt] = c[nt][0]; y[2 * nt + 1] = c[nt][1]; }
+}
+
+__device__ __forceinline__ double group_sum(double v)   // over the 4 lanes of a chunk
+{
+    v += __shfl_xor_sync(kAll, v, 1);
+    v += __shfl_xor_sync(kAll, v, 2);
+    return v;
+}
+
+// ---- fragment tables (built once per E-step) ------------------------------------------------------------
+__global__ void k_setup_frags(Model m)
+{
+    const int NE = m.n_eig, K = m.K;
+    const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+    double *F_Td = const_cast<double *>(m.F_Td), *F_P = const_cast<double *>(m.F_P), *F_PT = const_cast<double *>(m.F_PT),
+           *F_Pinv = const_cast<double *>(m.F_Pinv), *F_PinvT = const_cast<double *>(m.F_PinvT);
+    // F_W[(kt*4 + nt)*32 + lane] = W(8 nt + r, st(q, kt)),  lane = 4 r + q
+    for (long x = tid; x < (long)(1 + NE) * 1024; x += nth) {
+        const int mat = (int)(x >> 10), y = (int)(x & 1023);
+        const int kt = y >> 7, nt = (y >> 5) & 3, lane = y & 31, r = lane >> 2, q = lane & 3;
+        const int j = 8 * nt + r, i = st_of(q, kt);
+        if (mat == 0) {
+            F_Td[y] = m.Td[j * 32 + i];
+        } else {
+            const int e = mat - 1;
+            const double *P = m.P + (size_t)e * 1024, *Pinv = m.Pinv + (size_t)e * 1024;
+            F_P[(size_t)e * 1024 + y] = P[j * 32 + i];
+            F_PT[(size_t)e * 1024 + y] = P[i * 32 + j];
+            F_Pinv[(size_t)e * 1024 + y] = Pinv[j * 32 + i];
+            F_PinvT[(size_t)e * 1024 + y] = Pinv[i * 32 + j];
+        }
+    }
+    // q-major permuted vectors: v_q[q*8 + idx] = v[st(q, idx)]
+    double *Eq = const_cast<double *>(m.Eq), *dscq = const_cast<double *>(m.dscq), *logdq = const_cast<double *>(m.logdq);
+    for (long x = tid; x < (long)K * 32; x += nth) {
+        const int k = (int)(x >> 5), y = (int)(x & 31);
+        Eq[x] = m.E[(size_t)k * 32 + st_of(y >> 3, y & 7)];
+    }
+    for (long x = tid; x < (long)NE * 32; x += nth) {
+        const int e = (int)(x >> 5), y = (int)(x & 31);
+        dscq[x] = m.dsc[e * 32 + st_of(y >> 3, y & 7)];
+        logdq[x] = m.logd[e * 32 + st_of(y >> 3, y & 7)];
+    }
+    // step matrices: A32q[((k*32 + i)*4 + q)*8 + idx] = fl32(e_k(j) Td(i,j)), j = st(q, idx)
+    float *A32q = const_cast<float *>(m.A32q);
+    for (long x = tid; x < (long)K * 1024; x += nth) {
+        const int idx = (int)(x & 7), q = (int)((x >> 3) & 3), i = (int)((x >> 5) & 31), k = (int)(x >> 10);
+        A32q[x] = m.A32[(size_t)k * 1024 + i * 32 + st_of(q, idx)];
+    }
+}
+
+void launch_setup_frags(const Model &m, cudaStream_t st)
+{
+    long work = (long)m.K * 1024;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    k_setup_frags<<<blocks, 256, 0, st>>>(m);
+}
+
+// ---- shared per-chunk bookkeeping -------------------------------------------------------------------------
+struct ObsBatch {          // (span, code) of 8 consecutive blocks of the lane's chunk: lane q holds blocks q and 4 + q
+    int sp_lo, sp_hi, kc_lo, kc_hi;
+};
+
+// =============================================== forward ===================================================
+__global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w, int G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sF_Pinv = reinterpret_cast<double *>(smem_raw);       // [1024] hot eigen key
+    double *sF_P = sF_Pinv + 1024;                                // [1024]
+    double *s_dscq = sF_P + 1024, *s_logdq = s_dscq + 32;         // [32] each (q-major)
+    float *s_x = reinterpret_cast<float *>(s_logdq + 32);         // [kMW][8][36] (row stride 36 floats: fewer bank conflicts)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = lane >> 2, q = lane & 3;
+    const int hot = m.hot_eig;
+    if (hot >= 0) {
+        for (int x = tid; x < 1024; x += kMW * 32) {
+            sF_Pinv[x] = m.F_Pinv[(size_t)hot * 1024 + x];
+            sF_P[x] = m.F_P[(size_t)hot * 1024 + x];
+        }
+        if (tid < 32) { s_dscq[tid] = m.dscq[hot * 32 + tid]; s_logdq[tid] = m.logdq[hot * 32 + tid]; }
+    }
+    __syncthreads();
+    float *xs = s_x + ((size_t)warp * 8 + n) * 36;   // this chunk's row
+    const int M = m.M;
+
+    // G (<= 8) chunks per warp: small inputs spread over more warps (rows n >= G of the MMA stay idle)
+    const int c = n < G ? (blockIdx.x * kMW + warp) * G + n : p.n_chunks;
+    bool active = c < p.n_chunks;
+    const int cc = active ? c : 0;
+    const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
+    const int64_t g0 = p.blk_off[t];
+    const int bend = s + len;
+    float *acol = w.alpha + (p.col_off[t] + (int64_t)(cc - p.chunk_off[t]) * (p.chunk_blocks + 1)) * 32;
+    int cur = s - p.burn_in;
+    if (cur < 0) cur = 0;
+
+    float x[8];
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) x[idx] = (float)m.pi[st_of(q, idx)];   // reference src/hmm.cpp:59 (pads are 0)
+    auto store_col = [&](float *dst) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<float2 *>(dst + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
+    };
+    if (active && cur == s) { store_col(acol); store_col(w.start_used + (size_t)c * 32); }
+
+    int base = cur;
+    ObsBatch ob;
+    auto load_batch = [&](int b) {
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0;
+        if (b + q < bend) { ob.sp_lo = p.span[g0 + b + q]; ob.kc_lo = p.kcode[g0 + b + q]; }
+        if (b + 4 + q < bend) { ob.sp_hi = p.span[g0 + b + 4 + q]; ob.kc_hi = p.kcode[g0 + b + 4 + q]; }
+    };
+    if (active) load_batch(base); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; }
+    double llsum = 0.0, lprod = 1.0;
+    int lcnt = 0, done = 0, rounds = 0;
+
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        ++rounds;
+        const int pos = cur - base;
+        const int src = (lane & ~3) | (pos & 3);
+        const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
+        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int type = active ? (kc >> 11) : -1;
+        // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
+        const int k = adv ? (kc & 2047) : 0;
+        float xn[8];
+        double cmul = 1.0, cadd = 0.0;
+        float sf = 0.f;
+        if (T > 0) {
+            // a = P_r (d~^span o (Pinv_r alpha_prev)); reference src/hmm.cpp:74-80
+            const int e = T - 1;
+            double xd[8], u[8], a[8];
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) xd[idx] = (double)x[idx];
+            const double *dq, *lq;
+            if (e == hot) { gemv8<true>(sF_Pinv, xd, u, lane); dq = s_dscq; lq = s_logdq; }
+            else { gemv8<false>(m.F_Pinv + (size_t)e * 1024, xd, u, lane); dq = m.dscq + e * 32; lq = m.logdq + e * 32; }
+            const int sp = adv ? span : 1;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) u[idx] *= pow_span(dq[q * 8 + idx], lq[q * 8 + idx], sp);
+            if (e == hot) gemv8<true>(sF_P, u, a, lane); else gemv8<false>(m.F_P + (size_t)e * 1024, u, a, lane);
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) part += a[idx];
+            const double ssum = group_sum(part);
+            const double rs = 1.0 / ssum;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) xn[idx] = (float)(a[idx] * rs);
+            cmul = ssum;
+            cadd = (double)sp * m.logscale[e];
+        } else {
+            // float GEMV, k-sequential axpy order with the float-rounded matrix; reference src/hmm.cpp:85-89
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
+            __syncwarp();
+            const float4 *xr = reinterpret_cast<const float4 *>(xs);
+            const float4 *A = reinterpret_cast<const float4 *>(m.A32q + ((size_t)k * 128 + q) * 8);   // + i*8 float4 per row i
+            float y[8];
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) y[idx] = 0.f;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 xv = xr[i4];
+#pragma unroll
+                for (int cidx = 0; cidx < 4; ++cidx) {
+                    const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
+                    const int i = 4 * i4 + cidx;
+                    const float4 a0 = __ldg(A + i * 8), a1 = __ldg(A + i * 8 + 1);
+                    y[0] = __fadd_rn(y[0], __fmul_rn(xi, a0.x)); y[1] = __fadd_rn(y[1], __fmul_rn(xi, a0.y));
+                    y[2] = __fadd_rn(y[2], __fmul_rn(xi, a0.z)); y[3] = __fadd_rn(y[3], __fmul_rn(xi, a0.w));
+                    y[4] = __fadd_rn(y[4], __fmul_rn(xi, a1.x)); y[5] = __fadd_rn(y[5], __fmul_rn(xi, a1.y));
+                    y[6] = __fadd_rn(y[6], __fmul_rn(xi, a1.z)); y[7] = __fadd_rn(y[7], __fmul_rn(xi, a1.w));
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
+            __syncwarp();
+            sf = eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) xn[idx] = __fdiv_rn(y[idx], sf);
+            cmul = (double)sf;
+        }
+        if (adv) {
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) {
+                float v = xn[idx];
+                if (st_of(q, idx) < M && v < 1e-10f) v = 1e-10f;     // reference src/hmm.cpp:92-94
+                x[idx] = v;
+            }
+            if (cur >= s) {
+                store_col(acol + (size_t)(cur - s + 1) * 32);
+                lprod *= cmul;
+                llsum += cadd;
+                if (++lcnt == 8 || !(lprod > 1e-200)) { llsum += log(lprod); lprod = 1.0; lcnt = 0; }
+                if (T == 0 && q == 0) w.cnorm[g0 + cur] = sf;
+            } else if (cur == s - 1) {
+                store_col(acol);
+                store_col(w.start_used + (size_t)c * 32);
+            }
+            ++cur;
+            ++done;
+            if (cur >= bend) active = false;
+            else if (cur - base == 8) { base += 8; load_batch(base); }
+        }
+    }
+    if (c < p.n_chunks) {
+        store_col(w.end_alpha + (size_t)c * 32);
+        if (q == 0) w.ll_chunk[c] = llsum + log(lprod);
+    }
+    if (lane == 0) atomicAdd(&w.counters[4], rounds);                 // diagnostics: lockstep efficiency
+    if (q == 0 && c < p.n_chunks) atomicAdd(&w.counters[5], done);
+}
+
+// =============================================== backward ==================================================
+__global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work w, int G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sF_Td = reinterpret_cast<double *>(smem_raw);        // [1024]
+    double *sF_PT = sF_Td + 1024, *sF_PinvT = sF_PT + 1024;      // [1024] each, hot eigen key
+    double *s_dscq = sF_PinvT + 1024, *s_logdq = s_dscq + 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = lane >> 2, q = lane & 3;
+    const int hot = m.hot_eig;
+    for (int x = tid; x < 1024; x += kMW * 32) {
+        sF_Td[x] = m.F_Td[x];
+        if (hot >= 0) { sF_PT[x] = m.F_PT[(size_t)hot * 1024 + x]; sF_PinvT[x] = m.F_PinvT[(size_t)hot * 1024 + x]; }
+    }
+    if (hot >= 0 && tid < 32) { s_dscq[tid] = m.dscq[hot * 32 + tid]; s_logdq[tid] = m.logdq[hot * 32 + tid]; }
+    __syncthreads();
+    const int M = m.M;
+
+    const int c = n < G ? (blockIdx.x * kMW + warp) * G + n : p.n_chunks;
+    bool active = c < p.n_chunks;
+    const int cc = active ? c : 0;
+    const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
+    const int64_t g0 = p.blk_off[t];
+    const int L = (int)(p.blk_off[t + 1] - g0);
+    const int bend = s + len;
+    int b1 = bend + p.burn_in;
+    if (b1 > L || bend == L) b1 = L;
+    int cur = b1 - 1;                         // block processed next (descending)
+
+    double beta[8];
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) beta[idx] = st_of(q, idx) < M ? 1.0 : 0.0;   // reference src/hmm.cpp:97
+    auto store_vec = [&](double *dst, const double (&v)[8], double mul) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<double2 *>(dst + 8 * nt + 2 * q) = make_double2(v[2 * nt] * mul, v[2 * nt + 1] * mul);
+    };
+
+    int top = cur;                            // batch = blocks top, top-1, ..., top-7; lane q holds top-q and top-4-q
+    ObsBatch ob;
+    auto load_batch = [&](int tp) {
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0;
+        if (tp - q >= s) { ob.sp_lo = p.span[g0 + tp - q]; ob.kc_lo = p.kcode[g0 + tp - q]; }
+        if (tp - 4 - q >= s) { ob.sp_hi = p.span[g0 + tp - 4 - q]; ob.kc_hi = p.kcode[g0 + tp - 4 - q]; }
+    };
+    if (active) load_batch(top); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; }
+    int since = 0, done = 0;
+
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        const int pos = top - cur;
+        const int src = (lane & ~3) | (pos & 3);
+        const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
+        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int type = active ? (kc >> 11) : -1;
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
+        const int k = adv ? (kc & 2047) : 0;
+        // the chunk's verified start value: normalised, recorded before the first stored step
+        const bool rec = adv && cur == bend - 1;
+        if (__any_sync(kAll, rec)) {
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) part += beta[idx];
+            const double bs = group_sum(part);
+            if (rec) {
+                const double rb = 1.0 / bs;
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) beta[idx] *= rb;
+                store_vec(w.bstart_used + (size_t)c * 32, beta, 1.0);
+            }
+        }
+        const bool storing = adv && cur < bend;
+        double *bv = w.bvec + (size_t)(g0 + (adv ? cur : 0)) * 32;
+        double nb[8];
+        if (T > 0) {
+            // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
+            const int e = T - 1;
+            double wv[8];
+            const double *dq, *lq;
+            if (e == hot) { gemv8<true>(sF_PT, beta, wv, lane); dq = s_dscq; lq = s_logdq; }
+            else { gemv8<false>(m.F_PT + (size_t)e * 1024, beta, wv, lane); dq = m.dscq + e * 32; lq = m.logdq + e * 32; }
+            if (storing) store_vec(bv, wv, 1.0);
+            const int sp = adv ? span : 1;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) wv[idx] *= pow_span(dq[q * 8 + idx], lq[q * 8 + idx], sp);
+            if (e == hot) gemv8<true>(sF_PinvT, wv, nb, lane); else gemv8<false>(m.F_PinvT + (size_t)e * 1024, wv, nb, lane);
+        } else {
+            // beta <- Td (e_k o beta); reference src/hmm.cpp:139
+            if (storing) store_vec(bv, beta, 1.0);
+            const double2 *eq = reinterpret_cast<const double2 *>(m.Eq + (size_t)k * 32 + q * 8);
+            double tv[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const double2 ev = __ldg(eq + h);
+                tv[2 * h] = ev.x * beta[2 * h];
+                tv[2 * h + 1] = ev.y * beta[2 * h + 1];
+            }
+            gemv8<true>(sF_Td, tv, nb, lane);
+        }
+        // loose normalisation by an exact power of two (every statistic is invariant to beta's scale)
+        ++since;
+        bool tiny = true;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) tiny = tiny && !(fabs(nb[idx]) > 1e-100);
+        const int t1 = __shfl_xor_sync(kAll, (int)tiny, 1), t2 = __shfl_xor_sync(kAll, (int)tiny, 2), t3 = __shfl_xor_sync(kAll, (int)tiny, 3);
+        const bool need = adv && (since >= 4 || (t1 & t2 & t3 & (int)tiny));
+        if (__any_sync(kAll, need)) {
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) part += nb[idx];
+            const double f = pow2_rescale(group_sum(part));
+            if (need) {
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) nb[idx] *= f;
+                since = 0;
+            }
+        }
+        if (adv) {
+#pragma unroll
+            for (int idx = 0; idx < 8; ++idx) beta[idx] = nb[idx];
+            --cur;
+            ++done;
+            if (cur < s) active = false;
+            else if (top - cur == 8) { top -= 8; load_batch(top); }
+        } else {
+            --since;
+        }
+    }
+    if (c < p.n_chunks) {
+        double part = 0.0;
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) part += beta[idx];
+        const double bs = group_sum(part);
+        store_vec(w.beta_out + (size_t)c * 32, beta, 1.0 / bs);
+    } else {
+        group_sum(0.0);
+    }
+}
+
+size_t fwd32m_smem() { return (2 * 1024 + 64) * sizeof(double) + (size_t)kMW * 8 * 36 * sizeof(float); }
+size_t bwd32m_smem() { return (3 * 1024 + 64) * sizeof(double); }
+
+int resident_warps32m(int n_sm)
+{
+    int bf = 0, bb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward32m, kMW * 32, fwd32m_smem());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward32m, kMW * 32, bwd32m_smem());
+    int b = bf < bb ? bf : bb;
+    if (b < 1) b = 1;
+    return n_sm * b * kMW;
+}
+
+// chunks per warp: 8 when there are enough chunks to give every SM `want` warps, fewer otherwise
+static int chunks_per_warp(int n_chunks, int n_sm)
+{
+    const int want = n_sm * 2;
+    int G = 8;
+    while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
+    return G;
+}
+
+void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+{
+    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int warps = (p.n_chunks + G - 1) / G;
+    k_forward32m<<<(warps + kMW - 1) / kMW, kMW * 32, fwd32m_smem(), st>>>(m, p, w, G);
+}
+
+void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+{
+    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int warps = (p.n_chunks + G - 1) / G;
+    k_backward32m<<<(warps + kMW - 1) / kMW, kMW * 32, bwd32m_smem(), st>>>(m, p, w, G);
+}
+
+}  // namespace smcb

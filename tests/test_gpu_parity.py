@@ -60,6 +60,16 @@ def test_golden_chunked(name, chunk, burn):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if Golden(n).M <= 32])
+@pytest.mark.parametrize("chunk,burn", [(64, 64), (100, 512), (37, 300), (16, 0)])
+def test_golden_chunked_tensor_path(name, chunk, burn):
+    """The 8-chunks-per-warp DMMA recursions (recursion32_mma.cu), forced on for small inputs."""
+    g = Golden(name)
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": chunk, "burn_in_blocks": burn, "mma_min_chunks": 1})
+    check_against(out, g.ref)
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["c1_2k", "c2_1500", "m17_800", "m64_600", "ref_test_inference"])
 def test_golden_library_eigensystems(name):
     g = Golden(name)
@@ -114,7 +124,7 @@ def test_fresh_inputs_against_port(M, n, L):
     if eig["eig_cplx"].any():
         pytest.skip("random chain has complex eigenvalues")
     ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
-    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512})
+    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1 if M % 2 else 64})
     for c, obs in enumerate(w.contigs):
         o = port.hmm_estep(obs, ref)
         assert abs(out["ll"][c] - o["ll"]) <= LL_RTOL * abs(o["ll"])
@@ -142,7 +152,7 @@ def test_errors_follow_the_reference():
     with pytest.raises(RuntimeError, match="missing from the explicit key table"):
         ctx.set_contigs([ok], 1, np.array([[-1, 0, 0], [0, 0, 0]], np.int32))
     with pytest.raises(RuntimeError, match="set_contigs"):
-        ctx.estep(np.ones(4) / 4, np.eye(4), np.ones((1, 4)))
+        ctx.estep(np.ones(4) / 4, np.eye(4), np.ones((0, 4)))     # no contigs yet (K = 0)
     ctx.set_contigs([ok], 1)
     with pytest.raises(ValueError):
         ctx.estep(np.ones(4) / 4, np.eye(4), np.ones((2, 4)))     # K = 3
