@@ -133,6 +133,7 @@ typedef struct smcpp_b200_stats_t {
     int32_t kernel_launches; /* CUDA kernels launched by the last estep() */
     float ms_setup, ms_forward, ms_backward, ms_stats, ms_finalize, ms_total; /* CUDA-event times */
     double fwd_max_mismatch, bwd_max_mismatch;
+    float ms_forward_only;         /* forward pass 0 alone; ms_forward = both recursions incl. sweeps, ms_backward = backward pass 0 alone */
     int32_t mma_rounds, mma_steps; /* tensor-path forward kernel: warp rounds and committed chunk-steps (efficiency = steps / (8 rounds)) */
 } smcpp_b200_stats_t;
 int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out);

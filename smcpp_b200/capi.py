@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
                 ("ms_setup", ctypes.c_float), ("ms_forward", ctypes.c_float), ("ms_backward", ctypes.c_float),
                 ("ms_stats", ctypes.c_float), ("ms_finalize", ctypes.c_float), ("ms_total", ctypes.c_float),
                 ("fwd_max_mismatch", ctypes.c_double), ("bwd_max_mismatch", ctypes.c_double),
-                ("mma_rounds", ctypes.c_int32), ("mma_steps", ctypes.c_int32)]
+                ("ms_forward_only", ctypes.c_float), ("mma_rounds", ctypes.c_int32), ("mma_steps", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -119,6 +119,11 @@ class Context:
         self.C = 0
         self.K = 0
         self.M = 0
+        # tuning knobs for experiments: SMCPP_B200_OPTS="target_warps=2368,burn_in_blocks=768"
+        for item in os.environ.get("SMCPP_B200_OPTS", "").split(","):
+            if "=" in item:
+                k, v = item.split("=", 1)
+                self.set_option(k.strip(), float(v))
 
     def close(self):
         if self._h:

@@ -86,10 +86,11 @@ struct smcpp_b200_ctx {
     std::vector<int32_t> eig_keys;    // n_eig key indices (ascending = the reference's map order)
     std::vector<int32_t> eig_of_key;  // K
     std::vector<uint8_t> present;     // C x K
-    std::vector<int32_t> h_span;
+    std::vector<int32_t> h_span, h_span_id, span_list;
     std::vector<uint16_t> h_key;     // packed code: key id | (1 + eigen index) << 11 for span > 1 blocks
     int hot_eig = -1;
-    DevBuf<int32_t> d_span;
+    DevBuf<int32_t> d_span, d_span_id, d_span_list;
+    DevBuf<double> m_pwtab;
     DevBuf<uint16_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
@@ -102,7 +103,7 @@ struct smcpp_b200_ctx {
     int opt_burn_in = 512;
     int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
     int n_sm = 148;
-    int opt_slab_blocks = 2048;
+    int opt_slab_blocks = 8192;
     double opt_fwd_tol = 4e-7, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
     int opt_force_sequential = 0;
@@ -146,6 +147,7 @@ struct smcpp_b200_ctx {
         m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
         m.F_Td = m_F_Td.p; m.F_P = m_F_P.p; m.F_PT = m_F_PT.p; m.F_Pinv = m_F_Pinv.p; m.F_PinvT = m_F_PinvT.p;
         m.Eq = m_Eq.p; m.dscq = m_dscq.p; m.logdq = m_logdq.p; m.A32q = m_A32q.p;
+        m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size();
         return m;
     }
     Plan plan() const
@@ -154,7 +156,7 @@ struct smcpp_b200_ctx {
         p.n_contigs = C; p.n_chunks = n_chunks; p.n_slabs = n_slabs;
         p.chunk_blocks = plan_Lc; p.burn_in = plan_burn; p.slab_blocks = plan_slab;
         p.total_blocks = total;
-        p.span = d_span.p; p.kcode = d_key.p;
+        p.span = d_span.p; p.kcode = d_key.p; p.span_id = d_span_id.p;
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
         p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
         p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
@@ -234,7 +236,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     // DevBuf / PinBuf members are released explicitly (they are plain structs without destructors)
-    ctx->d_span.release(); ctx->d_key.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
+    ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
     ctx->d_sl_mask.release(); ctx->d_perm.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
@@ -362,6 +364,9 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     // pass 2: per-block span / key id, per-contig presence
     ctx->h_span.resize(ctx->total);
     ctx->h_key.resize(ctx->total);
+    ctx->h_span_id.assign(ctx->total, 0);
+    ctx->span_list.clear();
+    std::unordered_map<int32_t, int32_t> span_index;
     ctx->present.assign((size_t)n_contigs * K, 0);
     std::vector<int64_t> eig_count(std::max(1, ctx->n_eig), 0);
     for (int c = 0; c < n_contigs; ++c) {
@@ -379,6 +384,14 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
             }
             ctx->h_span[g0 + l] = row[0];
             const int e = row[0] > 1 ? ctx->eig_of_key[last_id] : -1;
+            if (row[0] > 1) {
+                auto it = span_index.find(row[0]);
+                if (it == span_index.end()) {
+                    it = span_index.emplace(row[0], (int32_t)ctx->span_list.size()).first;
+                    ctx->span_list.push_back(row[0]);
+                }
+                ctx->h_span_id[g0 + l] = it->second;
+            }
             ctx->h_key[g0 + l] = (uint16_t)(last_id | ((e + 1) << 11));
             if (e >= 0) ++eig_count[e];
             ctx->present[(size_t)c * K + last_id] = 1;
@@ -391,6 +404,12 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     CU(ctx->d_key.ensure(ctx->total));
     CU(cudaMemcpy(ctx->d_span.p, ctx->h_span.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_key.p, ctx->h_key.data(), ctx->total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (ctx->span_list.empty()) ctx->span_list.push_back(2);   // keeps the table non-empty; never referenced
+    CU(ctx->d_span_id.ensure(ctx->total));
+    CU(cudaMemcpy(ctx->d_span_id.p, ctx->h_span_id.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(ctx->d_span_list.ensure(ctx->span_list.size()));
+    CU(cudaMemcpy(ctx->d_span_list.p, ctx->span_list.data(), ctx->span_list.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    std::vector<int32_t>().swap(ctx->h_span_id);
     CU(ctx->d_blk_off.ensure(n_contigs + 1));
     CU(cudaMemcpy(ctx->d_blk_off.p, ctx->blk_off.data(), (n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(ctx->d_eig_of_key.ensure(K));
@@ -556,6 +575,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->m_dr.ensure((size_t)NE * Mp));
     CU(ctx->m_scale.ensure(NE));
     CU(ctx->m_logscale.ensure(NE));
+    CU(ctx->m_pwtab.ensure((size_t)NE * ctx->span_list.size() * Mp));
     if (Mp == 32) {
         CU(ctx->m_A32q.ensure((size_t)K * 1024));
         CU(ctx->m_F_Td.ensure(1024));
@@ -641,7 +661,9 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         const double *di = ctx->d_in.p;
         launch_setup(ctx->model(), di + o_pi, di + o_T, di + o_E, di + o_P, di + o_Pi, di + o_d, di + o_ds, di + o_sc, ctx->st);
         ctx->stats.kernel_launches = 1;
-        if (ctx->Mp == 32) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 2; }
+        launch_setup_pwtab(ctx->model(), ctx->st);
+        ctx->stats.kernel_launches = 2;
+        if (ctx->Mp == 32) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 3; }
     } else {
         cudaEventRecord(ctx->ev[0], ctx->st);
         ctx->stats.kernel_launches = 0;
@@ -654,6 +676,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     cudaEventRecord(ctx->ev_setup_done, ctx->st);
     // backward recursion runs concurrently on the second stream (it does not depend on alpha)
     CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
+    cudaEventRecord(ctx->ev[5], ctx->st2);
     const bool mma = m.Mp == 32 && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
     ctx->use_mma = mma;
     if (mma) launch_backward32m(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
@@ -662,6 +685,8 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     if (mma) launch_forward32m(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
     launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
     ctx->stats.kernel_launches += 4;
+    cudaEventRecord(ctx->ev[7], ctx->st);
+    cudaEventRecord(ctx->ev[6], ctx->st2);
     cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0));
     int fwd_sweeps = 1, bwd_sweeps = 1, fwd_redone = 0, bwd_redone = 0;
@@ -727,7 +752,8 @@ static int finish_timing(smcpp_b200_ctx *ctx)
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.ms_setup = ms;
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_forward = ms;  // forward || backward + sweeps
-    ctx->stats.ms_backward = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->stats.ms_backward = ms;   // backward pass 0 alone (second stream)
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[7]); ctx->stats.ms_forward_only = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_stats = ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_finalize = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stats.ms_total = ms;

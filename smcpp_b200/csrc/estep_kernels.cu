@@ -769,6 +769,29 @@ void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t 
     k_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(m, p, w);
 }
 
+// d~^span for every (eigen key, distinct span): Model::pwtab
+__global__ void k_setup_pwtab(Model m)
+{
+    const int Mp = m.Mp;
+    const long n = (long)m.n_eig * m.n_span * Mp;
+    double *tab = const_cast<double *>(m.pwtab);
+    for (long x = blockIdx.x * (long)blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) {
+        const int a = (int)(x % Mp);
+        const long es = x / Mp;
+        const int sid = (int)(es % m.n_span), e = (int)(es / m.n_span);
+        tab[x] = pow_span(m.dsc[(size_t)e * Mp + a], m.logd[(size_t)e * Mp + a], m.span_list[sid]);
+    }
+}
+
+void launch_setup_pwtab(const Model &m, cudaStream_t st)
+{
+    const long n = (long)m.n_eig * m.n_span * m.Mp;
+    if (n <= 0) return;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_setup_pwtab<<<blocks, 256, 0, st>>>(m);
+}
+
 // debug tap: contiguous [L+1][M] alpha_hat of one contig
 __global__ void k_gather_alpha(Model m, Plan p, Work w, int t, float *out)
 {

@@ -49,6 +49,11 @@ struct Model {
     const double *dscq;      // [n_eig][32]
     const double *logdq;     // [n_eig][32]
     const float *A32q;       // [K][32][4][8]
+    // d~^span tables: one row per (eigen key, distinct span) -- the reference tabulates per (span, key) too
+    // (span_Qs, src/transition_bundle.cpp:29-58); rows are built per E-step by k_setup_pwtab
+    const double *pwtab;     // [n_eig][n_span][Mp]
+    const int32_t *span_list;// [n_span] distinct spans > 1 of the data set
+    int n_span;
 };
 
 // Static per-dataset layout (set_contigs) + per-plan chunking.
@@ -59,6 +64,7 @@ struct Plan {
     // per block (concatenated over contigs)
     const int32_t *span;     // [total]
     const uint16_t *kcode;   // [total]  bits 0-10: key id; bits 11-15: 1 + eigen index if span > 1, else 0
+    const int32_t *span_id;  // [total]  index into Model::span_list (0 for span-1 blocks)
     // per contig
     const int64_t *blk_off;  // [C+1] first global block of contig
     const int64_t *col_off;  // [C]   first alpha column of contig (chunk c at col_off + c*(chunk_blocks+1))
@@ -116,6 +122,7 @@ void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, c
 size_t sums_stride(const Model &m);
 int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
+void launch_setup_pwtab(const Model &m, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
 void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp == 32, pass 0, <= 8 chunks / warp
 void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);

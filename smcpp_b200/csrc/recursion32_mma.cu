@@ -115,8 +115,8 @@ void launch_setup_frags(const Model &m, cudaStream_t st)
 }
 
 // ---- shared per-chunk bookkeeping -------------------------------------------------------------------------
-struct ObsBatch {          // (span, code) of 8 consecutive blocks of the lane's chunk: lane q holds blocks q and 4 + q
-    int sp_lo, sp_hi, kc_lo, kc_hi;
+struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of the lane's chunk: lane q holds blocks q and 4 + q
+    int sp_lo, sp_hi, kc_lo, kc_hi, id_lo, id_hi;
 };
 
 // =============================================== forward ===================================================
@@ -164,11 +164,11 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
     int base = cur;
     ObsBatch ob;
     auto load_batch = [&](int b) {
-        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0;
-        if (b + q < bend) { ob.sp_lo = p.span[g0 + b + q]; ob.kc_lo = p.kcode[g0 + b + q]; }
-        if (b + 4 + q < bend) { ob.sp_hi = p.span[g0 + b + 4 + q]; ob.kc_hi = p.kcode[g0 + b + 4 + q]; }
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+        if (b + q < bend) { ob.sp_lo = p.span[g0 + b + q]; ob.kc_lo = p.kcode[g0 + b + q]; ob.id_lo = p.span_id[g0 + b + q]; }
+        if (b + 4 + q < bend) { ob.sp_hi = p.span[g0 + b + 4 + q]; ob.kc_hi = p.kcode[g0 + b + 4 + q]; ob.id_hi = p.span_id[g0 + b + 4 + q]; }
     };
-    if (active) load_batch(base); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; }
+    if (active) load_batch(base); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
     double llsum = 0.0, lprod = 1.0;
     int lcnt = 0, done = 0, rounds = 0;
 
@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
         const int src = (lane & ~3) | (pos & 3);
         const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
         const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
         const int type = active ? (kc >> 11) : -1;
         // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
@@ -195,12 +196,17 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
             double xd[8], u[8], a[8];
 #pragma unroll
             for (int idx = 0; idx < 8; ++idx) xd[idx] = (double)x[idx];
-            const double *dq, *lq;
-            if (e == hot) { gemv8<true>(sF_Pinv, xd, u, lane); dq = s_dscq; lq = s_logdq; }
-            else { gemv8<false>(m.F_Pinv + (size_t)e * 1024, xd, u, lane); dq = m.dscq + e * 32; lq = m.logdq + e * 32; }
+            if (e == hot) gemv8<true>(sF_Pinv, xd, u, lane); else gemv8<false>(m.F_Pinv + (size_t)e * 1024, xd, u, lane);
             const int sp = adv ? span : 1;
+            {   // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent)
+                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * 32) + q;
 #pragma unroll
-            for (int idx = 0; idx < 8; ++idx) u[idx] *= pow_span(dq[q * 8 + idx], lq[q * 8 + idx], sp);
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double2 v = __ldg(pw + 4 * nt);
+                    u[2 * nt] *= v.x;
+                    u[2 * nt + 1] *= v.y;
+                }
+            }
             if (e == hot) gemv8<true>(sF_P, u, a, lane); else gemv8<false>(m.F_P + (size_t)e * 1024, u, a, lane);
             double part = 0.0;
 #pragma unroll
@@ -316,11 +322,11 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
     int top = cur;                            // batch = blocks top, top-1, ..., top-7; lane q holds top-q and top-4-q
     ObsBatch ob;
     auto load_batch = [&](int tp) {
-        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0;
-        if (tp - q >= s) { ob.sp_lo = p.span[g0 + tp - q]; ob.kc_lo = p.kcode[g0 + tp - q]; }
-        if (tp - 4 - q >= s) { ob.sp_hi = p.span[g0 + tp - 4 - q]; ob.kc_hi = p.kcode[g0 + tp - 4 - q]; }
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+        if (tp - q >= s) { ob.kc_lo = p.kcode[g0 + tp - q]; ob.id_lo = p.span_id[g0 + tp - q]; }
+        if (tp - 4 - q >= s) { ob.kc_hi = p.kcode[g0 + tp - 4 - q]; ob.id_hi = p.span_id[g0 + tp - 4 - q]; }
     };
-    if (active) load_batch(top); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; }
+    if (active) load_batch(top); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
     int since = 0, done = 0;
 
     for (;;) {
@@ -328,8 +334,8 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
         if (!am) break;
         const int pos = top - cur;
         const int src = (lane & ~3) | (pos & 3);
-        const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
         const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
         const int type = active ? (kc >> 11) : -1;
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
         const int T = __shfl_sync(kAll, type, lead & 31);
@@ -356,13 +362,17 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
             // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
             const int e = T - 1;
             double wv[8];
-            const double *dq, *lq;
-            if (e == hot) { gemv8<true>(sF_PT, beta, wv, lane); dq = s_dscq; lq = s_logdq; }
-            else { gemv8<false>(m.F_PT + (size_t)e * 1024, beta, wv, lane); dq = m.dscq + e * 32; lq = m.logdq + e * 32; }
+            if (e == hot) gemv8<true>(sF_PT, beta, wv, lane); else gemv8<false>(m.F_PT + (size_t)e * 1024, beta, wv, lane);
             if (storing) store_vec(bv, wv, 1.0);
-            const int sp = adv ? span : 1;
+            {
+                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * 32) + q;
 #pragma unroll
-            for (int idx = 0; idx < 8; ++idx) wv[idx] *= pow_span(dq[q * 8 + idx], lq[q * 8 + idx], sp);
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double2 v = __ldg(pw + 4 * nt);
+                    wv[2 * nt] *= v.x;
+                    wv[2 * nt + 1] *= v.y;
+                }
+            }
             if (e == hot) gemv8<true>(sF_PinvT, wv, nb, lane); else gemv8<false>(m.F_PinvT + (size_t)e * 1024, wv, nb, lane);
         } else {
             // beta <- Td (e_k o beta); reference src/hmm.cpp:139

@@ -54,7 +54,7 @@ __device__ __forceinline__ void store_acc(double *sm, const double (&acc)[4][4][
         }
 }
 
-__global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Work w)
+__global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, Work w)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = m.K, NE = m.n_eig;
@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Wor
     double *bnd = gs + (size_t)K * 32;                                      // [kS32Warps][2][32] boundary key sums
     double *dred = bnd + (size_t)kS32Warps * 2 * 32;                        // [kS32Warps][32]
     int *bkey = reinterpret_cast<int *>(dred + (size_t)kS32Warps * 32);     // [kS32Warps][2]
+    double *pinv_s = reinterpret_cast<double *>(bkey + kS32Warps * 2);      // [4 mt][8 kt][32 lanes] A fragments of Pinv_r
 
     const int Lc = p.chunk_blocks;
     const int64_t colbase = p.col_off[t];
@@ -210,21 +211,20 @@ __global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Wor
         const int l0 = seg[1 + e], l1 = seg[2 + e];
         const int ngrp = (l1 - l0 + 7) >> 3;
         const int gbeg = (int)((long)ngrp * warp / kS32Warps), gend = (int)((long)ngrp * (warp + 1) / kS32Warps);
-        // Pinv_r as A fragments: A[a = 8mt + r][i = 4kt + q]
-        double pinv_f[4][8];
+        // Pinv_r as A fragments in shared memory: A[a = 8mt + r][i = 4kt + q] at [(mt*8 + kt)*32 + lane]
         {
             const double *Pinv = m.Pinv + (size_t)e * 1024;
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int kt = 0; kt < 8; ++kt) pinv_f[mt][kt] = Pinv[(8 * mt + r) * 32 + 4 * kt + q];
+            for (int x = tid; x < 1024; x += kS32Warps * 32) {
+                const int ln = x & 31, kt = (x >> 5) & 7, mt = x >> 8;
+                pinv_s[x] = Pinv[(8 * mt + (ln >> 2)) * 32 + 4 * kt + (ln & 3)];
+            }
+            __syncthreads();
         }
-        double dsc[4], logd[4], invd[4];
+        double invd[4];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-            dsc[mt] = m.dsc[e * 32 + 8 * mt + r];
-            logd[mt] = m.logd[e * 32 + 8 * mt + r];
-            invd[mt] = dsc[mt] != 0.0 ? 1.0 / dsc[mt] : 0.0;
+            const double dv = m.dsc[e * 32 + 8 * mt + r];
+            invd[mt] = dv != 0.0 ? 1.0 / dv : 0.0;
         }
         const double sc = m.scale[e];
         double acc[4][4][2];
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Wor
                 for (int kt = 0; kt < 8; ++kt) {
                     const double bfr = vr ? (double)ap[4 * kt + q] : 0.0;
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) dmma884(u[mt][0], u[mt][1], pinv_f[mt][kt], bfr);
+                    for (int mt = 0; mt < 4; ++mt) dmma884(u[mt][0], u[mt][1], pinv_s[(mt * 8 + kt) * 32 + lane], bfr);
                 }
             }
             // per lane: blocks 2q + h, states 8mt + r
@@ -259,11 +259,12 @@ __global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Wor
                 const int64_t gb = g0 + b;
                 const int span = vb ? p.span[gb] : 2;
                 const double *bv = w.bvec + (size_t)gb * 32;
+                const double *pwr = m.pwtab + ((size_t)e * m.n_span + (vb ? p.span_id[gb] : 0)) * 32;
                 double wv[4], pw[4], dot = 0.0;
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) {
                     wv[mt] = vb ? bv[8 * mt + r] : 0.0;
-                    pw[mt] = pow_span(dsc[mt], logd[mt], span);
+                    pw[mt] = __ldg(pwr + 8 * mt + r);
                     dot = fma(pw[mt] * u[mt][h], wv[mt], dot);
                 }
                 dot = sum_over_r(dot);
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kS32Warps * 32) k_stats32(Model m, Plan p, Wor
 
 size_t stats32_smem_bytes(const Model &m)
 {
-    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32) * sizeof(double) +
+    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32 + 1024) * sizeof(double) +
            (size_t)kS32Warps * 2 * sizeof(int);
 }
 
