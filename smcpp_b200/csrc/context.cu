@@ -95,7 +95,8 @@ struct smcpp_b200_ctx {
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
     DevBuf<uint32_t> d_sl_mask;
-    DevBuf<int32_t> d_perm, d_seg;
+    DevBuf<int2> d_srec;
+    DevBuf<int32_t> d_seg;
     DevBuf<int> d_eig_of_key, d_key_of_eig;
 
     // ---- options
@@ -160,7 +161,7 @@ struct smcpp_b200_ctx {
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
         p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
         p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
-        p.perm = d_perm.p; p.seg = d_seg.p;
+        p.srec = d_srec.p; p.seg = d_seg.p;
         return p;
     }
     Work work() const
@@ -239,7 +240,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_perm.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
+    ctx->d_sl_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
@@ -409,7 +410,6 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     CU(cudaMemcpy(ctx->d_span_id.p, ctx->h_span_id.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(ctx->d_span_list.ensure(ctx->span_list.size()));
     CU(cudaMemcpy(ctx->d_span_list.p, ctx->span_list.data(), ctx->span_list.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    std::vector<int32_t>().swap(ctx->h_span_id);
     CU(ctx->d_blk_off.ensure(n_contigs + 1));
     CU(cudaMemcpy(ctx->d_blk_off.p, ctx->blk_off.data(), (n_contigs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(ctx->d_eig_of_key.ensure(K));
@@ -489,7 +489,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     ctx->col_off.assign(C, 0);
     std::vector<int32_t> ch_contig, ch_start, ch_len, sl_contig, sl_start, sl_len;
     std::vector<uint32_t> sl_mask;
-    std::vector<int32_t> perm(ctx->total), seg;
+    std::vector<int2> srec(ctx->total);
+    std::vector<int32_t> seg;
     std::vector<uint64_t> sortbuf;
     const int NEp = ctx->n_eig;
     int64_t cols = 0;
@@ -532,7 +533,11 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
                 while (at < sortbuf.size() && (int)(sortbuf[at] >> 48) == cls) ++at;
             }
             seg.push_back((int32_t)at);
-            for (int b = 0; b < n; ++b) perm[g0 + b] = (int32_t)(sortbuf[b] & 0xffffffffu);
+            for (int b = 0; b < n; ++b) {
+                const int32_t bi = (int32_t)(sortbuf[b] & 0xffffffffu);
+                const uint16_t kc = ctx->h_key[ctx->blk_off[c] + bi];
+                srec[g0 + b] = make_int2(bi, (kc >> 11) == 0 ? (int)(kc & 2047) : ctx->h_span_id[ctx->blk_off[c] + bi]);
+            }
         }
         ctx->slab_off[c + 1] = (int)sl_contig.size();
     }
@@ -556,7 +561,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     UP(d_sl_start, sl_start);
     UP(d_sl_len, sl_len);
     UP(d_sl_mask, sl_mask);
-    UP(d_perm, perm);
+    UP(d_srec, srec);
     UP(d_seg, seg);
 #undef UP
     const int K = ctx->K, NE = std::max(1, ctx->n_eig);

@@ -80,7 +80,7 @@ struct Plan {
     const int32_t *sl_len;   // [n_slabs]
     const uint32_t *sl_mask; // [n_slabs] bit0: has span-1 blocks; bit 1+e: has span>1 blocks of eigen key e
     // processing order of the statistics kernel: per slab [span-1 blocks sorted by key | eigen key 0 | eigen key 1 ...]
-    const int32_t *perm;     // [total]  block index within the contig, stored at the slab's own offset
+    const int2 *srec;        // [total]  (block index within the contig, key id for span-1 blocks / span id otherwise), at the slab's own offset
     const int32_t *seg;      // [n_slabs][n_eig + 2] segment boundaries (relative to the slab start)
 };
 

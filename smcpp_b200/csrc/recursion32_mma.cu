@@ -34,7 +34,7 @@ __device__ __forceinline__ int st_of(int q, int idx) { return 8 * (idx >> 1) + 2
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }

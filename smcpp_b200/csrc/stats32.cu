@@ -21,7 +21,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
     const int64_t g0 = p.blk_off[t];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
-    const int32_t *perm = p.perm + g0 + s0;                 // this slab's processing order (block index in contig)
+    const int2 *rec = p.srec + g0 + s0;   // this slab's processing order: (block index in contig, key id | span id)
     const int32_t *seg = p.seg + (size_t)slab * (NE + 2);   // [dense | eig 0 | eig 1 | ... ] offsets into perm
 
     double *tiles = reinterpret_cast<double *>(smem_raw);                   // [kS32Warps][32*33]
@@ -113,12 +113,15 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                 first_open = false;
             }
         };
+        // the (block index, key) record of the next group is fetched one iteration ahead: no dependent load chain
+        int2 rnext = (gbeg < gend && d0 + 4 * gbeg + q < d1) ? __ldg(rec + d0 + 4 * gbeg + q) : make_int2(0, -1);
         for (int g = gbeg; g < gend; ++g) {
-            const int pos = d0 + 4 * g + q;
-            const bool valid = pos < d1;
-            const int b = valid ? perm[pos] : 0;
+            const int2 rc = rnext;
+            rnext = (g + 1 < gend && d0 + 4 * (g + 1) + q < d1) ? __ldg(rec + d0 + 4 * (g + 1) + q) : make_int2(0, -1);
+            const bool valid = rc.y >= 0;
+            const int b = rc.x;
             const int64_t gb = g0 + b;
-            const int k = valid ? (p.kcode[gb] & 2047) : -1;
+            const int k = rc.y;
             double av[4], bvv[4], vv[4], be[4], ac[4], ek[4];
             double pp = 0.0, cn = 1.0;
             if (valid) {
@@ -233,15 +236,26 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+        int2 rBn = (gbeg < gend && l0 + 8 * gbeg + r < l1) ? __ldg(rec + l0 + 8 * gbeg + r) : make_int2(-1, 0);
+        int2 rHn0 = (gbeg < gend && l0 + 8 * gbeg + 2 * q < l1) ? __ldg(rec + l0 + 8 * gbeg + 2 * q) : make_int2(-1, 0);
+        int2 rHn1 = (gbeg < gend && l0 + 8 * gbeg + 2 * q + 1 < l1) ? __ldg(rec + l0 + 8 * gbeg + 2 * q + 1) : make_int2(-1, 0);
         for (int g = gbeg; g < gend; ++g) {
             const int base = l0 + 8 * g;
+            const int2 rB = rBn, rH0 = rHn0, rH1 = rHn1;
+            {
+                const int nb = base + 8;
+                const bool more = g + 1 < gend;
+                rBn = (more && nb + r < l1) ? __ldg(rec + nb + r) : make_int2(-1, 0);
+                rHn0 = (more && nb + 2 * q < l1) ? __ldg(rec + nb + 2 * q) : make_int2(-1, 0);
+                rHn1 = (more && nb + 2 * q + 1 < l1) ? __ldg(rec + nb + 2 * q + 1) : make_int2(-1, 0);
+            }
             // U = Pinv_r [alpha_prev of 8 blocks]: B[i = 4kt + q][block r]
             double u[4][2];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) u[mt][0] = u[mt][1] = 0.0;
             {
-                const bool vr = base + r < l1;
-                const int br = vr ? perm[base + r] : 0;
+                const bool vr = rB.x >= 0;
+                const int br = vr ? rB.x : 0;
                 const float *ap = alpha_col(br);
 #pragma unroll
                 for (int kt = 0; kt < 8; ++kt) {
@@ -254,12 +268,12 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
             double xs[4][2], ys[4][2], zs[4][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const bool vb = base + 2 * q + h < l1;
-                const int b = vb ? perm[base + 2 * q + h] : 0;
-                const int64_t gb = g0 + b;
-                const int span = vb ? p.span[gb] : 2;
+                const int2 rc = h == 0 ? rH0 : rH1;
+                const bool vb = rc.x >= 0;
+                const int64_t gb = g0 + (vb ? rc.x : 0);
+                const int span = vb ? __ldg(m.span_list + rc.y) : 2;
                 const double *bv = w.bvec + (size_t)gb * 32;
-                const double *pwr = m.pwtab + ((size_t)e * m.n_span + (vb ? p.span_id[gb] : 0)) * 32;
+                const double *pwr = m.pwtab + ((size_t)e * m.n_span + (vb ? rc.y : 0)) * 32;
                 double wv[4], pw[4], dot = 0.0;
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) {
