@@ -82,7 +82,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -234,7 +234,6 @@ def main():
             ms_tot.append(st["ms_total"])
     barrier()
     t_res = time.perf_counter() - t0
-    clocks = sampler.stop()
     ll_total = float(red[0].item())
     # ---- end-to-end arm
     for _ in range(2):
@@ -245,6 +244,8 @@ def main():
         step_e2e()
     barrier()
     t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+    e2e_stats = ctx.stats() if contigs else {}
 
     tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -273,7 +274,7 @@ def main():
                        "one_time_upload_s": upload_s},
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
             "e2e": {"value": e2e, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "device_ms_per_step": e2e_stats.get("ms_total")},
             "roofline": {"bound": "hbm", "kernel": "k_forward || k_backward (recursions, rank 0)", "achieved": ach, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms},

@@ -57,6 +57,25 @@ __device__ __forceinline__ void gemv8(const double *F, const double (&v)[8], dou
     for (int nt = 0; nt < 4; ++nt) { y[2 * nt] = c[nt][0]; y[2 * nt + 1] = c[nt][1]; }
 }
 
+// same with the B fragments of W held in registers (hot eigen key): no shared-memory traffic at all.
+// profiles/r1e: with fragments in shared memory the recursions are bound by the SM's one-wavefront-per-cycle
+// L1/shared pipe (one LDS.64 = 2 wavefronts per DMMA), not by the FP64 tensor pipe.
+template <int NF>
+__device__ __forceinline__ void gemv8_reg(const double (&F)[NF], const double (&v)[8], double (&y)[8])
+{
+    static_assert(NF == 32 || NF == 1, "fragment array");
+    if (NF != 32) return;   // never instantiated for real work
+    double c[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) c[nt][0] = c[nt][1] = 0.0;
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(c[nt][0], c[nt][1], v[kt], F[(kt * 4 + nt) % NF]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { y[2 * nt] = c[nt][0]; y[2 * nt + 1] = c[nt][1]; }
+}
+
 __device__ __forceinline__ double group_sum(double v)   // over the 4 lanes of a chunk
 {
     v += __shfl_xor_sync(kAll, v, 1);
@@ -120,24 +139,34 @@ struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of t
 };
 
 // =============================================== forward ===================================================
+// kReg: B fragments of the hot eigen key in registers (2 x 64 regs; at most 8 warps/SM, forward and backward then run
+// one after the other) or in shared memory (all warps of both kernels resident at once).  The launcher picks.
+template <bool kReg>
 __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w, int G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sF_Pinv = reinterpret_cast<double *>(smem_raw);       // [1024] hot eigen key
-    double *sF_P = sF_Pinv + 1024;                                // [1024]
-    double *s_dscq = sF_P + 1024, *s_logdq = s_dscq + 32;         // [32] each (q-major)
-    float *s_x = reinterpret_cast<float *>(s_logdq + 32);         // [kMW][8][36] (row stride 36 floats: fewer bank conflicts)
+    double *sF_Pinv = reinterpret_cast<double *>(smem_raw);       // [1024] + [1024], used when !kReg
+    double *sF_P = sF_Pinv + 1024;
+    float *s_x = reinterpret_cast<float *>(smem_raw + (kReg ? 0 : 2 * 1024 * sizeof(double)));   // [kMW][8][36]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = lane >> 2, q = lane & 3;
     const int hot = m.hot_eig;
-    if (hot >= 0) {
-        for (int x = tid; x < 1024; x += kMW * 32) {
-            sF_Pinv[x] = m.F_Pinv[(size_t)hot * 1024 + x];
-            sF_P[x] = m.F_P[(size_t)hot * 1024 + x];
+    // B fragments of Pinv_r and P_r of the hot eigen key: 2 x 32 doubles per lane, resident for the whole chunk
+    double rF_Pinv[kReg ? 32 : 1], rF_P[kReg ? 32 : 1];
+    if (kReg) {
+#pragma unroll
+        for (int f = 0; f < (kReg ? 32 : 1); ++f) {
+            rF_Pinv[f] = hot >= 0 ? m.F_Pinv[(size_t)hot * 1024 + f * 32 + lane] : 0.0;
+            rF_P[f] = hot >= 0 ? m.F_P[(size_t)hot * 1024 + f * 32 + lane] : 0.0;
         }
-        if (tid < 32) { s_dscq[tid] = m.dscq[hot * 32 + tid]; s_logdq[tid] = m.logdq[hot * 32 + tid]; }
+    } else {
+        if (hot >= 0)
+            for (int x = tid; x < 1024; x += kMW * 32) {
+                sF_Pinv[x] = m.F_Pinv[(size_t)hot * 1024 + x];
+                sF_P[x] = m.F_P[(size_t)hot * 1024 + x];
+            }
+        __syncthreads();
     }
-    __syncthreads();
     float *xs = s_x + ((size_t)warp * 8 + n) * 36;   // this chunk's row
     const int M = m.M;
 
@@ -196,7 +225,8 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
             double xd[8], u[8], a[8];
 #pragma unroll
             for (int idx = 0; idx < 8; ++idx) xd[idx] = (double)x[idx];
-            if (e == hot) gemv8<true>(sF_Pinv, xd, u, lane); else gemv8<false>(m.F_Pinv + (size_t)e * 1024, xd, u, lane);
+            if (e == hot) { if (kReg) gemv8_reg(rF_Pinv, xd, u); else gemv8<true>(sF_Pinv, xd, u, lane); }
+            else gemv8<false>(m.F_Pinv + (size_t)e * 1024, xd, u, lane);
             const int sp = adv ? span : 1;
             {   // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent)
                 const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * 32) + q;
@@ -207,7 +237,8 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
                     u[2 * nt + 1] *= v.y;
                 }
             }
-            if (e == hot) gemv8<true>(sF_P, u, a, lane); else gemv8<false>(m.F_P + (size_t)e * 1024, u, a, lane);
+            if (e == hot) { if (kReg) gemv8_reg(rF_P, u, a); else gemv8<true>(sF_P, u, a, lane); }
+            else gemv8<false>(m.F_P + (size_t)e * 1024, u, a, lane);
             double part = 0.0;
 #pragma unroll
             for (int idx = 0; idx < 8; ++idx) part += a[idx];
@@ -283,20 +314,26 @@ __global__ void __launch_bounds__(kMW * 32) k_forward32m(Model m, Plan p, Work w
 }
 
 // =============================================== backward ==================================================
+template <bool kReg>
 __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work w, int G)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sF_Td = reinterpret_cast<double *>(smem_raw);        // [1024]
-    double *sF_PT = sF_Td + 1024, *sF_PinvT = sF_PT + 1024;      // [1024] each, hot eigen key
-    double *s_dscq = sF_PinvT + 1024, *s_logdq = s_dscq + 32;
+    double *sF_Td = reinterpret_cast<double *>(smem_raw);        // [1024] B fragments of Td (span-1 rounds)
+    double *sF_PT = sF_Td + 1024, *sF_PinvT = sF_PT + 1024;      // [1024] each, used when !kReg
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = lane >> 2, q = lane & 3;
     const int hot = m.hot_eig;
-    for (int x = tid; x < 1024; x += kMW * 32) {
-        sF_Td[x] = m.F_Td[x];
-        if (hot >= 0) { sF_PT[x] = m.F_PT[(size_t)hot * 1024 + x]; sF_PinvT[x] = m.F_PinvT[(size_t)hot * 1024 + x]; }
+    for (int x = tid; x < 1024; x += kMW * 32) sF_Td[x] = m.F_Td[x];
+    double rF_PT[kReg ? 32 : 1], rF_PinvT[kReg ? 32 : 1];        // hot eigen key: P_r^T, Pinv_r^T fragments in registers
+    if (kReg) {
+#pragma unroll
+        for (int f = 0; f < (kReg ? 32 : 1); ++f) {
+            rF_PT[f] = hot >= 0 ? m.F_PT[(size_t)hot * 1024 + f * 32 + lane] : 0.0;
+            rF_PinvT[f] = hot >= 0 ? m.F_PinvT[(size_t)hot * 1024 + f * 32 + lane] : 0.0;
+        }
+    } else if (hot >= 0) {
+        for (int x = tid; x < 1024; x += kMW * 32) { sF_PT[x] = m.F_PT[(size_t)hot * 1024 + x]; sF_PinvT[x] = m.F_PinvT[(size_t)hot * 1024 + x]; }
     }
-    if (hot >= 0 && tid < 32) { s_dscq[tid] = m.dscq[hot * 32 + tid]; s_logdq[tid] = m.logdq[hot * 32 + tid]; }
     __syncthreads();
     const int M = m.M;
 
@@ -362,7 +399,8 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
             // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
             const int e = T - 1;
             double wv[8];
-            if (e == hot) gemv8<true>(sF_PT, beta, wv, lane); else gemv8<false>(m.F_PT + (size_t)e * 1024, beta, wv, lane);
+            if (e == hot) { if (kReg) gemv8_reg(rF_PT, beta, wv); else gemv8<true>(sF_PT, beta, wv, lane); }
+            else gemv8<false>(m.F_PT + (size_t)e * 1024, beta, wv, lane);
             if (storing) store_vec(bv, wv, 1.0);
             {
                 const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * 32) + q;
@@ -373,7 +411,8 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
                     wv[2 * nt + 1] *= v.y;
                 }
             }
-            if (e == hot) gemv8<true>(sF_PinvT, wv, nb, lane); else gemv8<false>(m.F_PinvT + (size_t)e * 1024, wv, nb, lane);
+            if (e == hot) { if (kReg) gemv8_reg(rF_PinvT, wv, nb); else gemv8<true>(sF_PinvT, wv, nb, lane); }
+            else gemv8<false>(m.F_PinvT + (size_t)e * 1024, wv, nb, lane);
         } else {
             // beta <- Td (e_k o beta); reference src/hmm.cpp:139
             if (storing) store_vec(bv, beta, 1.0);
@@ -427,14 +466,14 @@ __global__ void __launch_bounds__(kMW * 32) k_backward32m(Model m, Plan p, Work 
     }
 }
 
-size_t fwd32m_smem() { return (2 * 1024 + 64) * sizeof(double) + (size_t)kMW * 8 * 36 * sizeof(float); }
-size_t bwd32m_smem() { return (3 * 1024 + 64) * sizeof(double); }
+size_t fwd32m_smem(bool reg) { return (reg ? 0 : 2 * 1024 * sizeof(double)) + (size_t)kMW * 8 * 36 * sizeof(float); }
+size_t bwd32m_smem(bool reg) { return (reg ? 1 : 3) * 1024 * sizeof(double); }
 
 int resident_warps32m(int n_sm)
 {
     int bf = 0, bb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward32m, kMW * 32, fwd32m_smem());
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward32m, kMW * 32, bwd32m_smem());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward32m<false>, kMW * 32, fwd32m_smem(false));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward32m<false>, kMW * 32, bwd32m_smem(false));
     int b = bf < bb ? bf : bb;
     if (b < 1) b = 1;
     return n_sm * b * kMW;
@@ -449,18 +488,23 @@ static int chunks_per_warp(int n_chunks, int n_sm)
     return G;
 }
 
+// register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
+static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
+
 void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
 {
     const int G = chunks_per_warp(p.n_chunks, n_sm);
     const int warps = (p.n_chunks + G - 1) / G;
-    k_forward32m<<<(warps + kMW - 1) / kMW, kMW * 32, fwd32m_smem(), st>>>(m, p, w, G);
+    if (use_reg_frags(warps, n_sm)) k_forward32m<true><<<(warps + kMW - 1) / kMW, kMW * 32, fwd32m_smem(true), st>>>(m, p, w, G);
+    else k_forward32m<false><<<(warps + kMW - 1) / kMW, kMW * 32, fwd32m_smem(false), st>>>(m, p, w, G);
 }
 
 void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
 {
     const int G = chunks_per_warp(p.n_chunks, n_sm);
     const int warps = (p.n_chunks + G - 1) / G;
-    k_backward32m<<<(warps + kMW - 1) / kMW, kMW * 32, bwd32m_smem(), st>>>(m, p, w, G);
+    if (use_reg_frags(warps, n_sm)) k_backward32m<true><<<(warps + kMW - 1) / kMW, kMW * 32, bwd32m_smem(true), st>>>(m, p, w, G);
+    else k_backward32m<false><<<(warps + kMW - 1) / kMW, kMW * 32, bwd32m_smem(false), st>>>(m, p, w, G);
 }
 
 }  // namespace smcb
