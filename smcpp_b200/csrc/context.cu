@@ -676,6 +676,10 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     const Model m = ctx->model();
     const Plan p = ctx->plan();
     const Work w = ctx->work();
+    // Drain the (tiny) setup work before the two recursion kernels are enqueued on their two streams: when the
+    // backward stream is parked on an event behind still-running setup kernels, the forward kernel takes the
+    // whole GPU first and the two passes run back to back instead of side by side (measured: 14.8 ms vs 8.1 ms).
+    if (upload) CU(cudaStreamSynchronize(ctx->st));
     cudaEventRecord(ctx->ev[1], ctx->st);
     CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
     cudaEventRecord(ctx->ev_setup_done, ctx->st);

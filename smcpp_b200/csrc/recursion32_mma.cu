@@ -491,8 +491,23 @@ static int chunks_per_warp(int n_chunks, int n_sm)
 // register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
 static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
 
+// Forward and backward kernels must be able to share an SM: give all variants the same shared-memory carve-out,
+// otherwise the second kernel waits for the SMs to drain and the two passes run back to back.
+static void configure_once()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const int carve = 50;
+    cudaFuncSetAttribute(k_forward32m<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(k_forward32m<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(k_backward32m<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(k_backward32m<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+}
+
 void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
 {
+    configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm);
     const int warps = (p.n_chunks + G - 1) / G;
     if (use_reg_frags(warps, n_sm)) k_forward32m<true><<<(warps + kMW - 1) / kMW, kMW * 32, fwd32m_smem(true), st>>>(m, p, w, G);
@@ -501,6 +516,7 @@ void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, c
 
 void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
 {
+    configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm);
     const int warps = (p.n_chunks + G - 1) / G;
     if (use_reg_frags(warps, n_sm)) k_backward32m<true><<<(warps + kMW - 1) / kMW, kMW * 32, bwd32m_smem(true), st>>>(m, p, w, G);
