@@ -84,6 +84,28 @@ int smcpp_b200_host_eigensystems(int M, int K, int n_eig, const int32_t *eig_key
                                  double *scale, int32_t *cplx);
 
 /*
+ * Host builders of the per-E-step HMM inputs from the model (value parts; context-free, no GPU needed).
+ *   eta: n_pieces piecewise-constant sizes a[] with lengths s[] (what SMCModel.stepwise_values() hands to
+ *        setParams, reference smcpp/_smcpp.pyx:205-221); hidden_states: M+1 boundaries, last = inf.
+ * Replace: recompute_initial_distribution (reference src/inference_manager.cpp:56-69);
+ *          compute_transition / HJTransition (src/transition.cpp:133-262; 113-bit instead of 256-bit products);
+ *          recompute_emission_probs + incorporate_theta + construct_bins (src/inference_manager.cpp:329-482,
+ *          src/conditioned_sfs.cpp:100-148) with the conditioned SFS supplied by the caller as
+ *          sfs[M][na[0]+1][sfs_dim] (the reference's DummySFS contract, include/conditioned_sfs.h:46-67).
+ * host_emission fails with the reference's messages ("probability vector not in [0, 1]", "s<=0", ...).
+ */
+int smcpp_b200_host_initial_distribution(int M, const double *hidden_states, int n_pieces, const double *a,
+                                         const double *s, double *pi);
+int smcpp_b200_host_average_coal_times(int M, const double *hidden_states, int n_pieces, const double *a,
+                                       const double *s, double *out);
+int smcpp_b200_host_transition(int M, const double *hidden_states, int n_pieces, const double *a, const double *s,
+                               double rho, double *T);
+int smcpp_b200_host_emission(int npop, const int32_t *n, const int32_t *na, int M, const double *hidden_states,
+                             int n_pieces, const double *a, const double *s, double theta, double alpha,
+                             double pol_err, const double *sfs, int K, const int32_t *keys, double *E,
+                             char *errbuf, int errbuf_len);
+
+/*
  * One E-step over all contigs of this context.
  * Replaces: InferenceManager::Estep -> TransitionBundle::update(T, true) -> parallel_do(HMM::Estep)
  *           (reference src/inference_manager.cpp:108-114, src/transition_bundle.cpp:3-61,

@@ -40,6 +40,8 @@ SYMBOLS = [
     "smcpp_b200_set_option", "smcpp_b200_set_contigs", "smcpp_b200_num_keys", "smcpp_b200_get_keys",
     "smcpp_b200_num_eig_keys", "smcpp_b200_get_eig_keys", "smcpp_b200_get_key_present", "smcpp_b200_total_blocks",
     "smcpp_b200_eigensystems", "smcpp_b200_host_eig", "smcpp_b200_host_eigensystems", "smcpp_b200_estep",
+    "smcpp_b200_host_initial_distribution", "smcpp_b200_host_average_coal_times", "smcpp_b200_host_transition",
+    "smcpp_b200_host_emission",
     "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
     "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat",
 ]
@@ -105,6 +107,35 @@ def host_eigensystems(T: np.ndarray, E: np.ndarray, eig_key_idx: np.ndarray) -> 
                                             ptr(out["eig_cplx"], c_i32p))
     if rc:
         raise RuntimeError("smcpp_b200_host_eigensystems failed")
+    return out
+
+
+def host_model_inputs(hidden_states, model_a, model_s, theta, rho, alpha, pol_err, sfs, n, na, keys) -> dict:
+    """pi, transition and emission table of one E-step, built by the library's host routines (rows a3-a5 of
+    SURVEY 8a): the value parts of what the reference's do_dirty_work() produces."""
+    hs = np.ascontiguousarray(hidden_states, np.float64)
+    a = np.ascontiguousarray(model_a, np.float64); s = np.ascontiguousarray(model_s, np.float64)
+    sfs = np.ascontiguousarray(sfs, np.float64); keys = np.ascontiguousarray(keys, np.int32)
+    n = np.ascontiguousarray(np.atleast_1d(n), np.int32); na = np.ascontiguousarray(np.atleast_1d(na), np.int32)
+    M, P, K, npc = hs.shape[0] - 1, n.shape[0], keys.shape[0], a.shape[0]
+    out = {"pi": np.empty(M), "T": np.empty((M, M)), "E": np.empty((K, M)), "avg_coal_times": np.empty(M), "keys": keys}
+    L = lib()
+    D = ctypes.c_double
+    rc = L.smcpp_b200_host_initial_distribution(ctypes.c_int(M), ptr(hs, c_f64p), ctypes.c_int(npc), ptr(a, c_f64p), ptr(s, c_f64p),
+                                                ptr(out["pi"], c_f64p))
+    rc |= L.smcpp_b200_host_average_coal_times(ctypes.c_int(M), ptr(hs, c_f64p), ctypes.c_int(npc), ptr(a, c_f64p), ptr(s, c_f64p),
+                                               ptr(out["avg_coal_times"], c_f64p))
+    rc |= L.smcpp_b200_host_transition(ctypes.c_int(M), ptr(hs, c_f64p), ctypes.c_int(npc), ptr(a, c_f64p), ptr(s, c_f64p),
+                                       D(rho), ptr(out["T"], c_f64p))
+    if rc:
+        raise RuntimeError("smcpp_b200 host model builders failed")
+    err = ctypes.create_string_buffer(256)
+    rc = L.smcpp_b200_host_emission(ctypes.c_int(P), ptr(n, c_i32p), ptr(na, c_i32p), ctypes.c_int(M), ptr(hs, c_f64p),
+                                    ctypes.c_int(npc), ptr(a, c_f64p), ptr(s, c_f64p), D(theta), D(alpha), D(pol_err),
+                                    ptr(sfs, c_f64p), ctypes.c_int(K), ptr(keys, c_i32p), ptr(out["E"], c_f64p), err,
+                                    ctypes.c_int(256))
+    if rc:
+        raise RuntimeError(err.value.decode() or "smcpp_b200_host_emission failed")
     return out
 
 

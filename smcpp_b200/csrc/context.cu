@@ -4,6 +4,7 @@
 #include "../../include/smcpp_b200.h"
 #include "eigen_host.h"
 #include "estep_kernels.cuh"
+#include "model_host.h"
 
 #include <algorithm>
 #include <array>
@@ -792,6 +793,34 @@ int smcpp_b200_host_eigensystems(int M, int K, int n_eig, const int32_t *eig_key
 {
     if (M < 1 || K < 1 || n_eig < 0 || (n_eig && !eig_key_idx) || !T || !E) return 1;
     return smcb::host_eigensystems(M, K, n_eig, eig_key_idx, T, E, P, Pinv, d, d_scaled, scale, cplx, nullptr);
+}
+
+int smcpp_b200_host_initial_distribution(int M, const double *hs, int np, const double *a, const double *s, double *pi)
+{
+    if (M < 1 || np < 1 || !hs || !a || !s || !pi) return 1;
+    return smcb::host_initial_distribution(M, hs, np, a, s, pi);
+}
+int smcpp_b200_host_average_coal_times(int M, const double *hs, int np, const double *a, const double *s, double *out)
+{
+    if (M < 1 || np < 1 || !hs || !a || !s || !out) return 1;
+    return smcb::host_average_coal_times(M, hs, np, a, s, out);
+}
+int smcpp_b200_host_transition(int M, const double *hs, int np, const double *a, const double *s, double rho, double *T)
+{
+    if (M < 1 || np < 1 || !hs || !a || !s || !T) return 1;
+    return smcb::host_transition(M, hs, np, a, s, rho, T);
+}
+int smcpp_b200_host_emission(int npop, const int32_t *n, const int32_t *na, int M, const double *hs, int np, const double *a,
+                             const double *s, double theta, double alpha, double pol_err, const double *sfs, int K,
+                             const int32_t *keys, double *E, char *errbuf, int errbuf_len)
+{
+    if (npop < 1 || npop > 2 || !n || !na || M < 1 || !hs || !a || !s || !sfs || K < 1 || !keys || !E) return 1;
+    std::string msg;
+    const int rc = smcb::host_emission(npop, n, na, M, hs, np, a, s, theta, alpha, pol_err, sfs, K, keys, E, &msg);
+    if (rc && errbuf && errbuf_len > 0) {
+        std::snprintf(errbuf, errbuf_len, "%s", msg.c_str());
+    }
+    return rc;
 }
 
 int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)

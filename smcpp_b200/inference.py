@@ -67,6 +67,45 @@ class InferenceManager:
             raise RuntimeError("set_hmm_inputs: expected pi[M], transition[M,M], emission_probs[K,M]")
         self._inputs = (pi, T, E, eigensystems)
 
+    def set_model(self, model_a, model_s, theta, rho, alpha, sfs, n, na, polarization_error: float = 0.0):
+        """Build pi / transition / emission table from the model like the reference's do_dirty_work()
+        (src/inference_manager.cpp:213-229), through the library's host routines (include/smcpp_b200.h:
+        smcpp_b200_host_initial_distribution / _transition / _emission).
+
+        model_a, model_s : piecewise-constant sizes and piece lengths (setParams, smcpp/_smcpp.pyx:205-221)
+        theta, rho, alpha: setTheta / setRho / setAlpha (src/inference_manager.cpp:71-87)
+        sfs              : conditioned SFS per hidden state, [M, na[0]+1, sfs_dim] -- an INPUT of this path
+                           (the reference computes it in OnePopConditionedSFS / JointCSFS, out of scope here)."""
+        mi = capi.host_model_inputs(self.hidden_states, model_a, model_s, theta, rho, alpha, polarization_error, sfs, n, na,
+                                    self.keys)
+        self.set_hmm_inputs(mi["pi"], mi["T"], mi["E"])
+        return mi
+
+    def Q(self):
+        """Value parts of InferenceManager::Q() (reference src/inference_manager.cpp:116-126, src/hmm.cpp:155-193):
+        [sum log(pi) gamma0, sum_{nb=0 keys} log(e) gamma_sums, sum_{nb>0 keys} ..., sum log(T) xisum], summed over
+        contigs.  Before the first E-step the reference's HMM constructor has pre-filled gamma_sums with span * pi
+        (src/hmm.cpp:18-26) and zeroed the rest; so do we."""
+        if self._inputs is None:
+            raise RuntimeError("Q: set_hmm_inputs() / set_model() has not been called")
+        pi, T, E, _ = self._inputs
+        if self._out is None:
+            gs = np.zeros((self.K, self.M))
+            lut = {tuple(int(v) for v in k): i for i, k in enumerate(self.keys)}
+            for ob in self._obs:
+                uniq, inv = np.unique(ob[:, 1:], axis=0, return_inverse=True)
+                tot = np.bincount(inv.reshape(-1), weights=ob[:, 0].astype(np.float64), minlength=len(uniq))
+                for u, t in zip(uniq, tot):
+                    gs[lut[tuple(int(v) for v in u)]] += t * pi
+            g0 = np.zeros(self.M)
+            xi = np.zeros((self.M, self.M))
+        else:
+            r = parallel.unpack_reduced(self._out["reduced"], self.M, self.K)
+            gs, g0, xi = r["gamma_sums"], r["gamma0"], r["xisum"]
+        nb = self.keys[:, 2::3].sum(axis=1)
+        le = np.log(E) * gs
+        return np.array([np.dot(np.log(pi), g0), le[nb == 0].sum(), le[nb > 0].sum(), (np.log(T) * xi).sum()])
+
     def set_option(self, name, value):
         for c in self._ctx:
             if c is not None:
