@@ -276,7 +276,10 @@ def main():
             "e2e": {"value": e2e, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "device_ms_per_step": e2e_stats.get("ms_total")},
             "roofline": {"bound": "hbm", "kernel": "k_forward || k_backward (recursions, rank 0)", "achieved": ach, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / hbm_peak,
+                         # dram__bytes_read+write of k_forward32m + k_backward32m, one launch each (profiles/r1f_summary.md);
+                         # measured for this workload on one GPU only
+                         "traffic": 8.98e9 if (cfg == "C3" and world == 1) else None, "peak_source": peak_src,
                          "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms},
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
