@@ -126,7 +126,7 @@ struct smcpp_b200_ctx {
     PinBuf<double> h_in;
     DevBuf<double> m_pi, m_Td, m_TdT, m_E, m_P, m_PT, m_Pinv, m_PinvT, m_dsc, m_logd, m_dr, m_scale, m_logscale;
     DevBuf<float> m_A32, m_A32q;
-    DevBuf<double> m_F_Td, m_F_P, m_F_PT, m_F_Pinv, m_F_PinvT, m_Eq, m_dscq, m_logdq;
+    DevBuf<double> m_F_Td, m_F_P, m_F_PT, m_F_Pinv, m_F_PinvT, m_Eq;
     bool use_mma = false;
     DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
     DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
@@ -148,7 +148,7 @@ struct smcpp_b200_ctx {
         m.P = m_P.p; m.PT = m_PT.p; m.Pinv = m_Pinv.p; m.PinvT = m_PinvT.p;
         m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
         m.F_Td = m_F_Td.p; m.F_P = m_F_P.p; m.F_PT = m_F_PT.p; m.F_Pinv = m_F_Pinv.p; m.F_PinvT = m_F_PinvT.p;
-        m.Eq = m_Eq.p; m.dscq = m_dscq.p; m.logdq = m_logdq.p; m.A32q = m_A32q.p;
+        m.Eq = m_Eq.p; m.A32q = m_A32q.p;
         m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size();
         return m;
     }
@@ -247,7 +247,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
     ctx->m_dr.release(); ctx->m_scale.release(); ctx->m_logscale.release(); ctx->m_A32.release(); ctx->m_A32q.release();
     ctx->m_F_Td.release(); ctx->m_F_P.release(); ctx->m_F_PT.release(); ctx->m_F_Pinv.release(); ctx->m_F_PinvT.release();
-    ctx->m_Eq.release(); ctx->m_dscq.release(); ctx->m_logdq.release();
+    ctx->m_Eq.release();
     ctx->w_alpha.release(); ctx->w_cnorm.release(); ctx->w_start_used.release(); ctx->w_end_alpha.release();
     ctx->w_end_alpha_prev.release(); ctx->w_bvec.release(); ctx->w_ll_chunk.release(); ctx->w_bstart_used.release();
     ctx->w_beta_out.release(); ctx->w_beta_out_prev.release(); ctx->w_Xpart.release(); ctx->w_Rpart.release();
@@ -463,7 +463,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         // as many chunks as fit in ONE resident wave of the recursion kernels (a partial second wave would
         // double the time), but never shorter than the burn-in, which bounds the redundant work by 2x
         int target = ctx->opt_target_warps;
-        if (target <= 0) target = Mp == 32 ? std::min(resident_warps32m(ctx->n_sm), ctx->n_sm * 8) * 8 : ctx->n_sm * 16;
+        const bool tensor_path = Mp == 32 || Mp == 64 || Mp == 128;
+        if (target <= 0) target = tensor_path ? std::min(resident_warps_mma(ctx->n_sm, Mp), ctx->n_sm * 8) * 8 : ctx->n_sm * 16;
         auto chunks_for = [&](int64_t lc) {
             int64_t n = 0;
             for (int c = 0; c < ctx->C; ++c) n += (ctx->blk_off[c + 1] - ctx->blk_off[c] + lc - 1) / lc;
@@ -582,16 +583,14 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->m_scale.ensure(NE));
     CU(ctx->m_logscale.ensure(NE));
     CU(ctx->m_pwtab.ensure((size_t)NE * ctx->span_list.size() * Mp));
-    if (Mp == 32) {
-        CU(ctx->m_A32q.ensure((size_t)K * 1024));
-        CU(ctx->m_F_Td.ensure(1024));
-        CU(ctx->m_F_P.ensure((size_t)NE * 1024));
-        CU(ctx->m_F_PT.ensure((size_t)NE * 1024));
-        CU(ctx->m_F_Pinv.ensure((size_t)NE * 1024));
-        CU(ctx->m_F_PinvT.ensure((size_t)NE * 1024));
-        CU(ctx->m_Eq.ensure((size_t)K * 32));
-        CU(ctx->m_dscq.ensure((size_t)NE * 32));
-        CU(ctx->m_logdq.ensure((size_t)NE * 32));
+    if (Mp == 32 || Mp == 64 || Mp == 128) {
+        CU(ctx->m_A32q.ensure((size_t)K * MM));
+        CU(ctx->m_F_Td.ensure(MM));
+        CU(ctx->m_F_P.ensure((size_t)NE * MM));
+        CU(ctx->m_F_PT.ensure((size_t)NE * MM));
+        CU(ctx->m_F_Pinv.ensure((size_t)NE * MM));
+        CU(ctx->m_F_PinvT.ensure((size_t)NE * MM));
+        CU(ctx->m_Eq.ensure((size_t)K * Mp));
     }
     CU(ctx->w_alpha.ensure((size_t)cols * Mp));
     CU(ctx->w_cnorm.ensure(ctx->total));
@@ -669,7 +668,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         ctx->stats.kernel_launches = 1;
         launch_setup_pwtab(ctx->model(), ctx->st);
         ctx->stats.kernel_launches = 2;
-        if (ctx->Mp == 32) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 3; }
+        if (ctx->Mp == 32 || ctx->Mp == 64 || ctx->Mp == 128) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 3; }
     } else {
         cudaEventRecord(ctx->ev[0], ctx->st);
         ctx->stats.kernel_launches = 0;
@@ -687,12 +686,12 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     // backward recursion runs concurrently on the second stream (it does not depend on alpha)
     CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
     cudaEventRecord(ctx->ev[5], ctx->st2);
-    const bool mma = m.Mp == 32 && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
+    const bool mma = (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
     ctx->use_mma = mma;
-    if (mma) launch_backward32m(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
+    if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
     launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st2);
     // forward recursion
-    if (mma) launch_forward32m(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
+    if (mma && mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp)) launch_forward_mma(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
     launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
     ctx->stats.kernel_launches += 4;
     cudaEventRecord(ctx->ev[7], ctx->st);

@@ -38,17 +38,15 @@ struct Model {
     const double *dr;        // [n_eig][Mp] d_r
     const double *scale;     // [n_eig]
     const double *logscale;  // [n_eig]
-    // tensor-path (Mp == 32) operand tables, see recursion32_mma.cu: matrices in mma B-fragment order,
+    // tensor-path (Mp in {32, 64, 128}) operand tables, see recursion_mma.cu: matrices in mma B-fragment order,
     // vectors and the float step matrices permuted to the per-lane state order st(q, idx)
-    const double *F_Td;      // [1024]
-    const double *F_P;       // [n_eig][1024]  W = P_r
-    const double *F_PT;      // [n_eig][1024]  W = P_r^T
-    const double *F_Pinv;    // [n_eig][1024]  W = Pinv_r
-    const double *F_PinvT;   // [n_eig][1024]  W = Pinv_r^T
-    const double *Eq;        // [K][32]
-    const double *dscq;      // [n_eig][32]
-    const double *logdq;     // [n_eig][32]
-    const float *A32q;       // [K][32][4][8]
+    const double *F_Td;      // [Mp*Mp]
+    const double *F_P;       // [n_eig][Mp*Mp]  W = P_r
+    const double *F_PT;      // [n_eig][Mp*Mp]  W = P_r^T
+    const double *F_Pinv;    // [n_eig][Mp*Mp]  W = Pinv_r
+    const double *F_PinvT;   // [n_eig][Mp*Mp]  W = Pinv_r^T
+    const double *Eq;        // [K][Mp]
+    const float *A32q;       // [K][Mp][4][Mp/4]
     // d~^span tables: one row per (eigen key, distinct span) -- the reference tabulates per (span, key) too
     // (span_Qs, src/transition_bundle.cpp:29-58); rows are built per E-step by k_setup_pwtab
     const double *pwtab;     // [n_eig][n_span][Mp]
@@ -124,9 +122,10 @@ int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
 void launch_setup_pwtab(const Model &m, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
-void launch_forward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp == 32, pass 0, <= 8 chunks / warp
-void launch_backward32m(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);
-int resident_warps32m(int n_sm);
+void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp in {32, 64, 128}, pass 0, <= 8 chunks / warp
+void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);
+int resident_warps_mma(int n_sm, int Mp);
+bool mma_forward_pays(int n_chunks, int n_sm, int Mp);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);

@@ -1,0 +1,602 @@
+// smcpp_b200 -- forward / backward recursions on the FP64 tensor path, 8 chunks per warp (M <= 128; the text
+// below describes M <= 32, i.e. NS = 1; NS = Mp / 32 scales the tile counts).
+//
+// A GEMV of the recursion (y = W x, 32x32 double) for EIGHT independent chunks at once is one small GEMM,
+// Y[8 chunks][32] = X[8][32] W^T, i.e. 32 mma.sync.m8n8k4.f64 (SASS: DMMA) per warp instead of 8 x 32 DFMA + 8 x 16
+// broadcast loads: the chunk index is the m dimension, the operand matrix W sits in shared memory in
+// B-fragment order (one LDS.64 per DMMA, shared by every warp of the CTA) and the 8 chunks give the
+// instruction-level parallelism that one dependent chain per warp cannot (profiles/r1b: the one-chunk-per-warp
+// kernels issue 10-30 % of the time).
+//
+// Lane = 4n + q: n = chunk slot (row of A and C fragments), q = k-slot.  A lane holds, for its chunk, the 8 states
+//     st(q, idx) = 8 (idx / 2) + 2 q + (idx % 2),   idx = 0..7
+// which is exactly where mma puts C[n][8 nt + 2q + h] (idx = 2 nt + h).  Feeding those registers back as
+// A-fragment k-tile idx works because the k index of an MMA may be permuted freely as long as A and B agree: the
+// B fragments are built (k_setup_frags) for the state order st(q, idx).  So chained GEMVs need no shuffles.
+//
+// The 8 chunks of a warp advance in lockstep "rounds": every round has one block type (span-1, or span>1 with
+// eigen key e) -- the type of the first unfinished chunk -- and only chunks whose current block has that type
+// commit.  With the alternating run/site structure of real and synthetic contigs all 8 commit every round;
+// arbitrary data only loses efficiency, never correctness.
+//
+// Numerics: same reference semantics as recursion32.cu (float alpha_hat, fl32 step matrix, sequential axpy
+// order and Eigen's sum() order for the float normaliser, 1e-10f floor); the fp64 normalisation multiplies by
+// 1/sum instead of dividing and sums the 32 doubles in a different order (a 1e-16 relative effect; the
+// one-chunk kernels, used for the sequential mode and for repair sweeps, keep the reference's exact order).
+#include "device_utils.cuh"
+#include "estep_kernels.cuh"
+
+namespace smcb {
+
+constexpr int kMW = 4;             // warps per CTA
+constexpr unsigned kAll = 0xffffffffu;
+
+__device__ __forceinline__ int st_of(int q, int idx) { return 8 * (idx >> 1) + 2 * q + (idx & 1); }
+
+// fragment sources
+constexpr int kFragReg = 0, kFragShared = 1, kFragGlobal = 2;
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// y[chunk][.] = W x[chunk][.] for the 8 chunks of the warp; F = W in B-fragment order (shared or global):
+// F[(kt * 4NS + nt) * 32 + lane] = W(8 nt + r, st(q, kt)), 8NS k-tiles x 4NS n-tiles
+template <int NS, bool kShared>
+__device__ __forceinline__ void gemv8(const double *F, const double (&v)[8 * NS], double (&y)[8 * NS], int lane)
+{
+    double c[4 * NS][2];
+#pragma unroll
+    for (int nt = 0; nt < 4 * NS; ++nt) c[nt][0] = c[nt][1] = 0.0;
+#pragma unroll
+    for (int kt = 0; kt < 8 * NS; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 4 * NS; ++nt) {
+            const double b = kShared ? F[(kt * 4 * NS + nt) * 32 + lane] : __ldg(F + (kt * 4 * NS + nt) * 32 + lane);
+            dmma(c[nt][0], c[nt][1], v[kt], b);
+        }
+#pragma unroll
+    for (int nt = 0; nt < 4 * NS; ++nt) { y[2 * nt] = c[nt][0]; y[2 * nt + 1] = c[nt][1]; }
+}
+
+// same with the B fragments of W held in registers (NS = 1, hot eigen key): no shared-memory traffic at all
+template <int NF>
+__device__ __forceinline__ void gemv8_reg(const double (&F)[NF], const double (&v)[8], double (&y)[8])
+{
+    static_assert(NF == 32 || NF == 1, "fragment array");
+    double c[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) c[nt][0] = c[nt][1] = 0.0;
+    if (NF == 32) {
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma(c[nt][0], c[nt][1], v[kt], F[(kt * 4 + nt) % NF]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { y[2 * nt] = c[nt][0]; y[2 * nt + 1] = c[nt][1]; }
+}
+
+template <int NS, int FRAG, int NF>
+__device__ __forceinline__ void gemv_hot(const double (&R)[NF], const double *S, const double *Gm, const double (&v)[8 * NS],
+                                         double (&y)[8 * NS], int lane)
+{
+    if constexpr (FRAG == kFragReg) gemv8_reg(R, v, y);
+    else if constexpr (FRAG == kFragShared) gemv8<NS, true>(S, v, y, lane);
+    else gemv8<NS, false>(Gm, v, y, lane);
+}
+
+__device__ __forceinline__ double group_sum(double v)   // over the 4 lanes of a chunk
+{
+    v += __shfl_xor_sync(kAll, v, 1);
+    v += __shfl_xor_sync(kAll, v, 2);
+    return v;
+}
+
+// ---- fragment tables (built once per E-step) ------------------------------------------------------------
+__global__ void k_setup_frags(Model m)
+{
+    const int NE = m.n_eig, K = m.K, Mp = m.Mp, NS = Mp / 32, MM = Mp * Mp, NT = 4 * NS, NI = 8 * NS;
+    const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+    double *F_Td = const_cast<double *>(m.F_Td), *F_P = const_cast<double *>(m.F_P), *F_PT = const_cast<double *>(m.F_PT),
+           *F_Pinv = const_cast<double *>(m.F_Pinv), *F_PinvT = const_cast<double *>(m.F_PinvT);
+    // F_W[(kt*NT + nt)*32 + lane] = W(8 nt + r, st(q, kt)),  lane = 4 r + q
+    for (long x = tid; x < (long)(1 + NE) * MM; x += nth) {
+        const int mat = (int)(x / MM), y = (int)(x % MM);
+        const int lane = y & 31, f = y >> 5, nt = f % NT, kt = f / NT, r = lane >> 2, q = lane & 3;
+        const int j = 8 * nt + r, i = st_of(q, kt);
+        if (mat == 0) {
+            F_Td[y] = m.Td[(size_t)j * Mp + i];
+        } else {
+            const int e = mat - 1;
+            const double *P = m.P + (size_t)e * MM, *Pinv = m.Pinv + (size_t)e * MM;
+            F_P[(size_t)e * MM + y] = P[(size_t)j * Mp + i];
+            F_PT[(size_t)e * MM + y] = P[(size_t)i * Mp + j];
+            F_Pinv[(size_t)e * MM + y] = Pinv[(size_t)j * Mp + i];
+            F_PinvT[(size_t)e * MM + y] = Pinv[(size_t)i * Mp + j];
+        }
+    }
+    // q-major permuted emission vectors: Eq[k][q*NI + idx] = E[k][st(q, idx)]
+    double *Eq = const_cast<double *>(m.Eq);
+    for (long x = tid; x < (long)K * Mp; x += nth) {
+        const int k = (int)(x / Mp), y = (int)(x % Mp);
+        Eq[x] = m.E[(size_t)k * Mp + st_of(y / NI, y % NI)];
+    }
+    // step matrices: A32q[((k*Mp + i)*4 + q)*NI + idx] = fl32(e_k(j) Td(i,j)), j = st(q, idx)
+    float *A32q = const_cast<float *>(m.A32q);
+    for (long x = tid; x < (long)K * MM; x += nth) {
+        const int idx = (int)(x % NI);
+        long rest = x / NI;
+        const int q = (int)(rest & 3);
+        rest >>= 2;
+        const int i = (int)(rest % Mp), k = (int)(rest / Mp);
+        A32q[x] = m.A32[(size_t)k * MM + (size_t)i * Mp + st_of(q, idx)];
+    }
+}
+
+void launch_setup_frags(const Model &m, cudaStream_t st)
+{
+    long work = (long)m.K * m.Mp * m.Mp;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    k_setup_frags<<<blocks, 256, 0, st>>>(m);
+}
+
+// ---- shared per-chunk bookkeeping -------------------------------------------------------------------------
+struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of the lane's chunk: lane q holds blocks q and 4 + q
+    int sp_lo, sp_hi, kc_lo, kc_hi, id_lo, id_hi;
+};
+
+// =============================================== forward ===================================================
+// FRAG: where the B fragments of the hot eigen key live -- registers (NS = 1 only: 2 x 64 registers, at most 8 warps/SM,
+// forward and backward then run one after the other), shared memory (all warps of both kernels resident at once) or
+// global memory through the read-only path (M = 128: a fragment table is 128 KB).  The launcher picks.
+template <int NS, int FRAG>
+__global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G)
+{
+    constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP, XS = MP + 4;
+    constexpr int NF = FRAG == kFragReg ? 32 : 1;
+    static_assert(FRAG != kFragReg || NS == 1, "register fragments need M <= 32");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sF_Pinv = reinterpret_cast<double *>(smem_raw);       // [MM] + [MM], used when FRAG == shared
+    double *sF_P = sF_Pinv + MM;
+    float *s_x = reinterpret_cast<float *>(smem_raw + (FRAG == kFragShared ? 2 * MM * sizeof(double) : 0));   // [kMW][8][XS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = lane >> 2, q = lane & 3;
+    const int hot = m.hot_eig;
+    double rF_Pinv[NF], rF_P[NF];
+    if constexpr (FRAG == kFragReg) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            rF_Pinv[f] = hot >= 0 ? m.F_Pinv[(size_t)hot * MM + f * 32 + lane] : 0.0;
+            rF_P[f] = hot >= 0 ? m.F_P[(size_t)hot * MM + f * 32 + lane] : 0.0;
+        }
+    } else {
+        rF_Pinv[0] = rF_P[0] = 0.0;
+        if constexpr (FRAG == kFragShared) {
+            if (hot >= 0)
+                for (int x = tid; x < MM; x += kMW * 32) {
+                    sF_Pinv[x] = m.F_Pinv[(size_t)hot * MM + x];
+                    sF_P[x] = m.F_P[(size_t)hot * MM + x];
+                }
+            __syncthreads();
+        }
+    }
+    float *xs = s_x + ((size_t)warp * 8 + n) * XS;   // this chunk's row (stride XS floats: fewer bank conflicts)
+    const int M = m.M;
+
+    // G (<= 8) chunks per warp: small inputs spread over more warps (rows n >= G of the MMA stay idle)
+    const int c = n < G ? (blockIdx.x * kMW + warp) * G + n : p.n_chunks;
+    bool active = c < p.n_chunks;
+    const int cc = active ? c : 0;
+    const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
+    const int64_t g0 = p.blk_off[t];
+    const int bend = s + len;
+    float *acol = w.alpha + (p.col_off[t] + (int64_t)(cc - p.chunk_off[t]) * (p.chunk_blocks + 1)) * MP;
+    int cur = s - p.burn_in;
+    if (cur < 0) cur = 0;
+
+    float x[NI];
+#pragma unroll
+    for (int idx = 0; idx < NI; ++idx) x[idx] = (float)m.pi[st_of(q, idx)];   // reference src/hmm.cpp:59 (pads are 0)
+    auto store_col = [&](float *dst) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(dst + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
+    };
+    if (active && cur == s) { store_col(acol); store_col(w.start_used + (size_t)c * MP); }
+
+    int base = cur;
+    ObsBatch ob;
+    auto load_batch = [&](int b) {
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+        if (b + q < bend) { ob.sp_lo = p.span[g0 + b + q]; ob.kc_lo = p.kcode[g0 + b + q]; ob.id_lo = p.span_id[g0 + b + q]; }
+        if (b + 4 + q < bend) { ob.sp_hi = p.span[g0 + b + 4 + q]; ob.kc_hi = p.kcode[g0 + b + 4 + q]; ob.id_hi = p.span_id[g0 + b + 4 + q]; }
+    };
+    if (active) load_batch(base); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
+    double llsum = 0.0, lprod = 1.0;
+    int lcnt = 0, done = 0, rounds = 0;
+
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        ++rounds;
+        const int pos = cur - base;
+        const int src = (lane & ~3) | (pos & 3);
+        const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
+        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
+        const int type = active ? (kc >> 11) : -1;
+        // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
+        const int k = adv ? (kc & 2047) : 0;
+        float xn[NI];
+        double cmul = 1.0, cadd = 0.0;
+        float sf = 0.f;
+        if (T > 0) {
+            // a = P_r (d~^span o (Pinv_r alpha_prev)); reference src/hmm.cpp:74-80
+            const int e = T - 1;
+            double xd[NI], u[NI], a[NI];
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) xd[idx] = (double)x[idx];
+            if (e == hot) gemv_hot<NS, FRAG>(rF_Pinv, sF_Pinv, m.F_Pinv + (size_t)e * MM, xd, u, lane);
+            else gemv8<NS, false>(m.F_Pinv + (size_t)e * MM, xd, u, lane);
+            const int sp = adv ? span : 1;
+            {   // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent)
+                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double2 v = __ldg(pw + 4 * nt);
+                    u[2 * nt] *= v.x;
+                    u[2 * nt + 1] *= v.y;
+                }
+            }
+            if (e == hot) gemv_hot<NS, FRAG>(rF_P, sF_P, m.F_P + (size_t)e * MM, u, a, lane);
+            else gemv8<NS, false>(m.F_P + (size_t)e * MM, u, a, lane);
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) part += a[idx];
+            const double ssum = group_sum(part);
+            const double rs = 1.0 / ssum;
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) xn[idx] = (float)(a[idx] * rs);
+            cmul = ssum;
+            cadd = (double)sp * m.logscale[e];
+        } else {
+            // float GEMV, k-sequential axpy order with the float-rounded matrix; reference src/hmm.cpp:85-89
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
+            __syncwarp();
+            const float4 *xr = reinterpret_cast<const float4 *>(xs);
+            const float4 *A = reinterpret_cast<const float4 *>(m.A32q + ((size_t)k * MP * 4 + q) * NI);   // row i: + i * NI float4
+            float y[NI];
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) y[idx] = 0.f;
+#pragma unroll(NS == 1 ? 8 : 2)
+            for (int i4 = 0; i4 < MP / 4; ++i4) {
+                const float4 xv = xr[i4];
+#pragma unroll
+                for (int cidx = 0; cidx < 4; ++cidx) {
+                    const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
+                    const float4 *Ai = A + (size_t)(4 * i4 + cidx) * NI;
+#pragma unroll
+                    for (int h = 0; h < 2 * NS; ++h) {
+                        const float4 av = __ldg(Ai + h);
+                        y[4 * h] = __fadd_rn(y[4 * h], __fmul_rn(xi, av.x));
+                        y[4 * h + 1] = __fadd_rn(y[4 * h + 1], __fmul_rn(xi, av.y));
+                        y[4 * h + 2] = __fadd_rn(y[4 * h + 2], __fmul_rn(xi, av.z));
+                        y[4 * h + 3] = __fadd_rn(y[4 * h + 3], __fmul_rn(xi, av.w));
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
+            __syncwarp();
+            sf = eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) xn[idx] = __fdiv_rn(y[idx], sf);
+            cmul = (double)sf;
+        }
+        if (adv) {
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) {
+                float v = xn[idx];
+                if (st_of(q, idx) < M && v < 1e-10f) v = 1e-10f;     // reference src/hmm.cpp:92-94
+                x[idx] = v;
+            }
+            if (cur >= s) {
+                store_col(acol + (size_t)(cur - s + 1) * MP);
+                lprod *= cmul;
+                llsum += cadd;
+                if (++lcnt == 8 || !(lprod > 1e-200)) { llsum += log(lprod); lprod = 1.0; lcnt = 0; }
+                if (T == 0 && q == 0) w.cnorm[g0 + cur] = sf;
+            } else if (cur == s - 1) {
+                store_col(acol);
+                store_col(w.start_used + (size_t)c * MP);
+            }
+            ++cur;
+            ++done;
+            if (cur >= bend) active = false;
+            else if (cur - base == 8) { base += 8; load_batch(base); }
+        }
+    }
+    if (c < p.n_chunks) {
+        store_col(w.end_alpha + (size_t)c * MP);
+        if (q == 0) w.ll_chunk[c] = llsum + log(lprod);
+    }
+    if (lane == 0) atomicAdd(&w.counters[4], rounds);                 // diagnostics: lockstep efficiency
+    if (q == 0 && c < p.n_chunks) atomicAdd(&w.counters[5], done);
+}
+
+// =============================================== backward ==================================================
+template <int NS, int FRAG>
+__global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work w, int G)
+{
+    constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP;
+    constexpr int NF = FRAG == kFragReg ? 32 : 1;
+    static_assert(FRAG != kFragReg || NS == 1, "register fragments need M <= 32");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Td fragments (span-1 rounds) are shared-resident unless everything is read from global memory (M = 128)
+    double *sF_Td = reinterpret_cast<double *>(smem_raw);        // [MM]
+    double *sF_PT = sF_Td + MM, *sF_PinvT = sF_PT + MM;          // [MM] each, used when FRAG == shared
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = lane >> 2, q = lane & 3;
+    const int hot = m.hot_eig;
+    double rF_PT[NF], rF_PinvT[NF];
+    if constexpr (FRAG != kFragGlobal) {
+        for (int x = tid; x < MM; x += kMW * 32) sF_Td[x] = m.F_Td[x];
+    }
+    if constexpr (FRAG == kFragReg) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            rF_PT[f] = hot >= 0 ? m.F_PT[(size_t)hot * MM + f * 32 + lane] : 0.0;
+            rF_PinvT[f] = hot >= 0 ? m.F_PinvT[(size_t)hot * MM + f * 32 + lane] : 0.0;
+        }
+    } else {
+        rF_PT[0] = rF_PinvT[0] = 0.0;
+        if constexpr (FRAG == kFragShared) {
+            if (hot >= 0)
+                for (int x = tid; x < MM; x += kMW * 32) { sF_PT[x] = m.F_PT[(size_t)hot * MM + x]; sF_PinvT[x] = m.F_PinvT[(size_t)hot * MM + x]; }
+        }
+    }
+    __syncthreads();
+    const int M = m.M;
+
+    const int c = n < G ? (blockIdx.x * kMW + (tid >> 5)) * G + n : p.n_chunks;
+    bool active = c < p.n_chunks;
+    const int cc = active ? c : 0;
+    const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
+    const int64_t g0 = p.blk_off[t];
+    const int L = (int)(p.blk_off[t + 1] - g0);
+    const int bend = s + len;
+    int b1 = bend + p.burn_in;
+    if (b1 > L || bend == L) b1 = L;
+    int cur = b1 - 1;                         // block processed next (descending)
+
+    double beta[NI];
+#pragma unroll
+    for (int idx = 0; idx < NI; ++idx) beta[idx] = st_of(q, idx) < M ? 1.0 : 0.0;   // reference src/hmm.cpp:97
+    auto store_vec = [&](double *dst, const double (&v)[NI], double mul) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<double2 *>(dst + 8 * nt + 2 * q) = make_double2(v[2 * nt] * mul, v[2 * nt + 1] * mul);
+    };
+
+    int top = cur;                            // batch = blocks top, top-1, ..., top-7; lane q holds top-q and top-4-q
+    ObsBatch ob;
+    auto load_batch = [&](int tp) {
+        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+        if (tp - q >= s) { ob.kc_lo = p.kcode[g0 + tp - q]; ob.id_lo = p.span_id[g0 + tp - q]; }
+        if (tp - 4 - q >= s) { ob.kc_hi = p.kcode[g0 + tp - 4 - q]; ob.id_hi = p.span_id[g0 + tp - 4 - q]; }
+    };
+    if (active) load_batch(top); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
+    int since = 0, done = 0;
+
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        const int pos = top - cur;
+        const int src = (lane & ~3) | (pos & 3);
+        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
+        const int type = active ? (kc >> 11) : -1;
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
+        const int k = adv ? (kc & 2047) : 0;
+        // the chunk's verified start value: normalised, recorded before the first stored step
+        const bool rec = adv && cur == bend - 1;
+        if (__any_sync(kAll, rec)) {
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) part += beta[idx];
+            const double bs = group_sum(part);
+            if (rec) {
+                const double rb = 1.0 / bs;
+#pragma unroll
+                for (int idx = 0; idx < NI; ++idx) beta[idx] *= rb;
+                store_vec(w.bstart_used + (size_t)c * MP, beta, 1.0);
+            }
+        }
+        const bool storing = adv && cur < bend;
+        double *bv = w.bvec + (size_t)(g0 + (adv ? cur : 0)) * MP;
+        double nb[NI];
+        if (T > 0) {
+            // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
+            const int e = T - 1;
+            double wv[NI];
+            if (e == hot) gemv_hot<NS, FRAG>(rF_PT, sF_PT, m.F_PT + (size_t)e * MM, beta, wv, lane);
+            else gemv8<NS, false>(m.F_PT + (size_t)e * MM, beta, wv, lane);
+            if (storing) store_vec(bv, wv, 1.0);
+            {
+                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double2 v = __ldg(pw + 4 * nt);
+                    wv[2 * nt] *= v.x;
+                    wv[2 * nt + 1] *= v.y;
+                }
+            }
+            if (e == hot) gemv_hot<NS, FRAG>(rF_PinvT, sF_PinvT, m.F_PinvT + (size_t)e * MM, wv, nb, lane);
+            else gemv8<NS, false>(m.F_PinvT + (size_t)e * MM, wv, nb, lane);
+        } else {
+            // beta <- Td (e_k o beta); reference src/hmm.cpp:139
+            if (storing) store_vec(bv, beta, 1.0);
+            const double2 *eq = reinterpret_cast<const double2 *>(m.Eq + (size_t)k * MP + q * NI);
+            double tv[NI];
+#pragma unroll
+            for (int h = 0; h < NI / 2; ++h) {
+                const double2 ev = __ldg(eq + h);
+                tv[2 * h] = ev.x * beta[2 * h];
+                tv[2 * h + 1] = ev.y * beta[2 * h + 1];
+            }
+            if constexpr (FRAG == kFragGlobal) gemv8<NS, false>(m.F_Td, tv, nb, lane);
+            else gemv8<NS, true>(sF_Td, tv, nb, lane);
+        }
+        // loose normalisation by an exact power of two (every statistic is invariant to beta's scale)
+        ++since;
+        bool tiny = true;
+#pragma unroll
+        for (int idx = 0; idx < NI; ++idx) tiny = tiny && !(fabs(nb[idx]) > 1e-100);
+        const int t1 = __shfl_xor_sync(kAll, (int)tiny, 1), t2 = __shfl_xor_sync(kAll, (int)tiny, 2), t3 = __shfl_xor_sync(kAll, (int)tiny, 3);
+        const bool need = adv && (since >= 4 || (t1 & t2 & t3 & (int)tiny));
+        if (__any_sync(kAll, need)) {
+            double part = 0.0;
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) part += nb[idx];
+            const double f = pow2_rescale(group_sum(part));
+            if (need) {
+#pragma unroll
+                for (int idx = 0; idx < NI; ++idx) nb[idx] *= f;
+                since = 0;
+            }
+        }
+        if (adv) {
+#pragma unroll
+            for (int idx = 0; idx < NI; ++idx) beta[idx] = nb[idx];
+            --cur;
+            ++done;
+            if (cur < s) active = false;
+            else if (top - cur == 8) { top -= 8; load_batch(top); }
+        } else {
+            --since;
+        }
+    }
+    if (c < p.n_chunks) {
+        double part = 0.0;
+#pragma unroll
+        for (int idx = 0; idx < NI; ++idx) part += beta[idx];
+        const double bs = group_sum(part);
+        store_vec(w.beta_out + (size_t)c * MP, beta, 1.0 / bs);
+    } else {
+        group_sum(0.0);
+    }
+}
+
+// ---- launch -------------------------------------------------------------------------------------------------
+static size_t fwd_smem(int NS, int frag)
+{
+    const size_t MP = 32 * NS;
+    return (frag == kFragShared ? 2 * MP * MP * sizeof(double) : 0) + (size_t)kMW * 8 * (MP + 4) * sizeof(float);
+}
+static size_t bwd_smem(int NS, int frag)
+{
+    const size_t MP = 32 * NS;
+    return frag == kFragGlobal ? 16 : (frag == kFragShared ? 3 : 1) * MP * MP * sizeof(double);
+}
+
+int resident_warps_mma(int n_sm, int Mp)
+{
+    int bf = 0, bb = 0;
+    if (Mp == 32) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<1, kFragShared>, kMW * 32, fwd_smem(1, kFragShared));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<1, kFragShared>, kMW * 32, bwd_smem(1, kFragShared));
+    } else if (Mp == 64) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<2, kFragShared>, kMW * 32, fwd_smem(2, kFragShared));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<2, kFragShared>, kMW * 32, bwd_smem(2, kFragShared));
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<4, kFragGlobal>, kMW * 32, fwd_smem(4, kFragGlobal));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<4, kFragGlobal>, kMW * 32, bwd_smem(4, kFragGlobal));
+    }
+    int b = bf < bb ? bf : bb;
+    if (b < 1) b = 1;
+    return n_sm * b * kMW;
+}
+
+// chunks per warp: 8 when there are enough chunks to give every SM `want` warps, fewer otherwise
+static int chunks_per_warp(int n_chunks, int n_sm)
+{
+    const int want = n_sm * 2;
+    int G = 8;
+    while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
+    return G;
+}
+
+// The tensor-path forward kernel gives each chunk only 4 lanes for the float GEMV of the span-1 step; above 32 states
+// that only pays off when every warp has its full 8 chunks, otherwise the one-chunk-per-warp kernel is used
+// (the backward pass has no float step and always takes the tensor path).
+bool mma_forward_pays(int n_chunks, int n_sm, int Mp) { return Mp == 32 || chunks_per_warp(n_chunks, n_sm) == 8; }
+
+// register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
+static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
+
+template <typename KF>
+static void set_attrs(KF kernel, size_t smem)
+{
+    // forward and backward kernels must be able to share an SM: the same shared-memory carve-out for every variant,
+    // otherwise the second kernel waits for the SMs to drain and the two passes run back to back
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+static void configure_once()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg));
+    set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared));
+    set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));
+    set_attrs(k_backward_mma<1, kFragShared>, bwd_smem(1, kFragShared));
+    set_attrs(k_forward_mma<2, kFragShared>, fwd_smem(2, kFragShared));
+    set_attrs(k_backward_mma<2, kFragShared>, bwd_smem(2, kFragShared));
+    set_attrs(k_forward_mma<4, kFragGlobal>, fwd_smem(4, kFragGlobal));
+    set_attrs(k_backward_mma<4, kFragGlobal>, bwd_smem(4, kFragGlobal));
+}
+
+void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+{
+    configure_once();
+    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    if (m.Mp == 32) {
+        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg), st>>>(m, p, w, G);
+        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared), st>>>(m, p, w, G);
+    } else if (m.Mp == 64) {
+        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared), st>>>(m, p, w, G);
+    } else {
+        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
+    }
+}
+
+void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+{
+    configure_once();
+    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    if (m.Mp == 32) {
+        if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, G);
+        else k_backward_mma<1, kFragShared><<<blocks, kMW * 32, bwd_smem(1, kFragShared), st>>>(m, p, w, G);
+    } else if (m.Mp == 64) {
+        k_backward_mma<2, kFragShared><<<blocks, kMW * 32, bwd_smem(2, kFragShared), st>>>(m, p, w, G);
+    } else {
+        k_backward_mma<4, kFragGlobal><<<blocks, kMW * 32, bwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
+    }
+}
+
+}  // namespace smcb

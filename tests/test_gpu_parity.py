@@ -60,7 +60,7 @@ def test_golden_chunked(name, chunk, burn):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if Golden(n).M <= 32])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)     # M = 16, 17, 32 (one 32-state tile), 51, 64 (two tiles)
 @pytest.mark.parametrize("chunk,burn", [(64, 64), (100, 512), (37, 300), (16, 0)])
 def test_golden_chunked_tensor_path(name, chunk, burn):
     """The 8-chunks-per-warp DMMA recursions (recursion32_mma.cu), forced on for small inputs."""
@@ -124,7 +124,7 @@ def test_fresh_inputs_against_port(M, n, L):
     if eig["eig_cplx"].any():
         pytest.skip("random chain has complex eigenvalues")
     ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
-    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1 if M % 2 else 64})
+    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1})
     for c, obs in enumerate(w.contigs):
         o = port.hmm_estep(obs, ref)
         assert abs(out["ll"][c] - o["ll"]) <= LL_RTOL * abs(o["ll"])
