@@ -36,8 +36,9 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device);
 void smcpp_b200_destroy(smcpp_b200_ctx *ctx);
 const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx); /* ctx may be NULL: error of the last failed create() */
 
-/* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks", "target_warps", "fwd_tol",
- * "bwd_tol", "max_sweeps", "force_sequential"}.  Returns non-zero for an unknown name. */
+/* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks", "target_warps", "slab_blocks", "fwd_tol",
+ * "bwd_tol", "max_sweeps", "force_sequential", "mma_min_chunks", "force_mma_forward"}.
+ * Returns non-zero for an unknown name. */
 int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value);
 
 /*

@@ -109,6 +109,7 @@ struct smcpp_b200_ctx {
     double opt_fwd_tol = 4e-7, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
     int opt_force_sequential = 0;
+    int opt_force_mma_forward = 0;  // tests: take the tensor-path forward kernel even where mma_forward_pays() says no
     int opt_mma_min_chunks = 64;    // use the 8-chunks-per-warp tensor-path recursions from this many chunks on
     int burn_in_adapt = 0;          // grows when boundary checks fail (sticky between E-steps)
 
@@ -277,6 +278,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
     else if (n == "max_sweeps") ctx->opt_max_sweeps = std::max(1, (int)value);
     else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
+    else if (n == "force_mma_forward") ctx->opt_force_mma_forward = value != 0;
     else if (n == "mma_min_chunks") ctx->opt_mma_min_chunks = std::max(1, (int)value);
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
@@ -691,7 +693,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
     launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st2);
     // forward recursion
-    if (mma && mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp)) launch_forward_mma(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
+    if (mma && (ctx->opt_force_mma_forward || mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp))) launch_forward_mma(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
     launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol, ctx->st);
     ctx->stats.kernel_launches += 4;
     cudaEventRecord(ctx->ev[7], ctx->st);

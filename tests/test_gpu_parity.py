@@ -65,7 +65,8 @@ def test_golden_chunked(name, chunk, burn):
 def test_golden_chunked_tensor_path(name, chunk, burn):
     """The 8-chunks-per-warp DMMA recursions (recursion32_mma.cu), forced on for small inputs."""
     g = Golden(name)
-    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": chunk, "burn_in_blocks": burn, "mma_min_chunks": 1})
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": chunk, "burn_in_blocks": burn, "mma_min_chunks": 1,
+                                                   "force_mma_forward": 1})
     check_against(out, g.ref)
     ctx.close()
 
@@ -124,7 +125,7 @@ def test_fresh_inputs_against_port(M, n, L):
     if eig["eig_cplx"].any():
         pytest.skip("random chain has complex eigenvalues")
     ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
-    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1})
+    ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": M % 2})
     for c, obs in enumerate(w.contigs):
         o = port.hmm_estep(obs, ref)
         assert abs(out["ll"][c] - o["ll"]) <= LL_RTOL * abs(o["ll"])
