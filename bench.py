@@ -198,10 +198,11 @@ def main():
     def step_resident():
         if contigs:
             ctx.estep_device(model["pi"], model["T"], model["E"], eig, upload=False)
-            ctx.copy_reduced_to_device(red.data_ptr(), nred)
+            ctx.copy_reduced_to_device(red.data_ptr(), nred)      # D2D on the context's stream, synchronised
         else:
             red.zero_()
         parallel.allreduce_sum_(red)
+        torch.cuda.current_stream().synchronize()                 # `red` is rewritten by the next step on another stream
 
     host_out = {}
 
@@ -213,7 +214,7 @@ def main():
         else:
             red.zero_()
         parallel.allreduce_sum_(red)
-        return red.cpu()
+        return red.cpu()                                          # D2H read of the reduced statistics (synchronises)
 
     # ---- warm-up (also uploads the per-step inputs once for the resident arm)
     if contigs:
@@ -235,6 +236,11 @@ def main():
     barrier()
     t_res = time.perf_counter() - t0
     ll_total = float(red[0].item())
+    # cross-check of the all-reduce: sum of the per-rank host-side log-likelihoods
+    own = torch.tensor([float(ctx.fetch()["ll"].sum()) if contigs else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(own)
+    ll_check = float(own.item())
     # ---- end-to-end arm
     for _ in range(2):
         step_e2e()
@@ -284,7 +290,7 @@ def main():
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
                               "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},
-            "loglik": ll_total, "chunks": ctx.stats()["n_chunks"], "sweeps": [ctx.stats()["fwd_sweeps"], ctx.stats()["bwd_sweeps"]],
+            "loglik": ll_total, "loglik_allreduce_check_rel": abs(ll_total - ll_check) / abs(ll_check), "chunks": ctx.stats()["n_chunks"], "sweeps": [ctx.stats()["fwd_sweeps"], ctx.stats()["bwd_sweeps"]],
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -89,6 +89,33 @@ __device__ __forceinline__ void gemv_hot(const double (&R)[NF], const double *S,
     else gemv8<NS, false>(Gm, v, y, lane);
 }
 
+struct float8 { float v[8]; };
+// one 256-bit read-only load (sm_100: LDG.E.256): 8 consecutive floats, 32-byte aligned
+__device__ __forceinline__ float8 ldg256(const float *p)
+{
+    float8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
+}
+
+// Eigen's float sum() order for exactly MPX = 32 NS aligned coefficients in shared memory (see eigen_sum_f32), unrolled
+template <int MPX>
+__device__ __forceinline__ float eigen_sum_f32_full(const float *v)
+{
+    const float4 *v4 = reinterpret_cast<const float4 *>(v);
+    float4 p0 = v4[0], p1 = v4[1];
+#pragma unroll
+    for (int qq = 1; qq < MPX / 8; ++qq) {
+        const float4 a = v4[2 * qq], b = v4[2 * qq + 1];
+        p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
+        p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
+    }
+    p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
+    return __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
+}
+
 __device__ __forceinline__ double group_sum(double v)   // over the 4 lanes of a chunk
 {
     v += __shfl_xor_sync(kAll, v, 1);
@@ -209,13 +236,17 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
     if (active && cur == s) { store_col(acol); store_col(w.start_used + (size_t)c * MP); }
 
     int base = cur;
-    ObsBatch ob;
+    ObsBatch ob, obn;                         // current batch of 8 blocks and the one after it (fetched a batch ahead)
     auto load_batch = [&](int b) {
-        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
-        if (b + q < bend) { ob.sp_lo = p.span[g0 + b + q]; ob.kc_lo = p.kcode[g0 + b + q]; ob.id_lo = p.span_id[g0 + b + q]; }
-        if (b + 4 + q < bend) { ob.sp_hi = p.span[g0 + b + 4 + q]; ob.kc_hi = p.kcode[g0 + b + 4 + q]; ob.id_hi = p.span_id[g0 + b + 4 + q]; }
+        ObsBatch o;
+        o.sp_lo = o.sp_hi = 1; o.kc_lo = o.kc_hi = 0; o.id_lo = o.id_hi = 0;
+        if (b + q < bend) { o.sp_lo = p.span[g0 + b + q]; o.kc_lo = p.kcode[g0 + b + q]; o.id_lo = p.span_id[g0 + b + q]; }
+        if (b + 4 + q < bend) { o.sp_hi = p.span[g0 + b + 4 + q]; o.kc_hi = p.kcode[g0 + b + 4 + q]; o.id_hi = p.span_id[g0 + b + 4 + q]; }
+        return o;
     };
-    if (active) load_batch(base); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
+    ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+    obn = ob;
+    if (active) { ob = load_batch(base); obn = load_batch(base + 8); }
     double llsum = 0.0, lprod = 1.0;
     int lcnt = 0, done = 0, rounds = 0;
 
@@ -241,20 +272,20 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             // a = P_r (d~^span o (Pinv_r alpha_prev)); reference src/hmm.cpp:74-80
             const int e = T - 1;
             double xd[NI], u[NI], a[NI];
+            // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent); issued before the first GEMV
+            double2 pwv[NT];
+            {
+                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + 4 * nt);
+            }
 #pragma unroll
             for (int idx = 0; idx < NI; ++idx) xd[idx] = (double)x[idx];
             if (e == hot) gemv_hot<NS, FRAG>(rF_Pinv, sF_Pinv, m.F_Pinv + (size_t)e * MM, xd, u, lane);
             else gemv8<NS, false>(m.F_Pinv + (size_t)e * MM, xd, u, lane);
             const int sp = adv ? span : 1;
-            {   // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent)
-                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double2 v = __ldg(pw + 4 * nt);
-                    u[2 * nt] *= v.x;
-                    u[2 * nt + 1] *= v.y;
-                }
-            }
+            for (int nt = 0; nt < NT; ++nt) { u[2 * nt] *= pwv[nt].x; u[2 * nt + 1] *= pwv[nt].y; }
             if (e == hot) gemv_hot<NS, FRAG>(rF_P, sF_P, m.F_P + (size_t)e * MM, u, a, lane);
             else gemv8<NS, false>(m.F_P + (size_t)e * MM, u, a, lane);
             double part = 0.0;
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
             __syncwarp();
             const float4 *xr = reinterpret_cast<const float4 *>(xs);
-            const float4 *A = reinterpret_cast<const float4 *>(m.A32q + ((size_t)k * MP * 4 + q) * NI);   // row i: + i * NI float4
+            const float *A = m.A32q + ((size_t)k * MP * 4 + q) * NI;   // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
             float y[NI];
 #pragma unroll
             for (int idx = 0; idx < NI; ++idx) y[idx] = 0.f;
@@ -283,14 +314,12 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 #pragma unroll
                 for (int cidx = 0; cidx < 4; ++cidx) {
                     const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
-                    const float4 *Ai = A + (size_t)(4 * i4 + cidx) * NI;
+                    const float *Ai = A + (size_t)(4 * i4 + cidx) * 4 * NI;
 #pragma unroll
-                    for (int h = 0; h < 2 * NS; ++h) {
-                        const float4 av = __ldg(Ai + h);
-                        y[4 * h] = __fadd_rn(y[4 * h], __fmul_rn(xi, av.x));
-                        y[4 * h + 1] = __fadd_rn(y[4 * h + 1], __fmul_rn(xi, av.y));
-                        y[4 * h + 2] = __fadd_rn(y[4 * h + 2], __fmul_rn(xi, av.z));
-                        y[4 * h + 3] = __fadd_rn(y[4 * h + 3], __fmul_rn(xi, av.w));
+                    for (int h = 0; h < NS; ++h) {
+                        const float8 av = ldg256(Ai + 8 * h);
+#pragma unroll
+                        for (int j8 = 0; j8 < 8; ++j8) y[8 * h + j8] = __fadd_rn(y[8 * h + j8], __fmul_rn(xi, av.v[j8]));
                     }
                 }
             }
@@ -298,7 +327,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
             __syncwarp();
-            sf = eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
+            sf = M == MP ? eigen_sum_f32_full<MP>(xs) : eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
 #pragma unroll
             for (int idx = 0; idx < NI; ++idx) xn[idx] = __fdiv_rn(y[idx], sf);
             cmul = (double)sf;
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             ++cur;
             ++done;
             if (cur >= bend) active = false;
-            else if (cur - base == 8) { base += 8; load_batch(base); }
+            else if (cur - base == 8) { base += 8; ob = obn; obn = load_batch(base + 8); }
         }
     }
     if (c < p.n_chunks) {
@@ -388,13 +417,17 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
     };
 
     int top = cur;                            // batch = blocks top, top-1, ..., top-7; lane q holds top-q and top-4-q
-    ObsBatch ob;
+    ObsBatch ob, obn;
     auto load_batch = [&](int tp) {
-        ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
-        if (tp - q >= s) { ob.kc_lo = p.kcode[g0 + tp - q]; ob.id_lo = p.span_id[g0 + tp - q]; }
-        if (tp - 4 - q >= s) { ob.kc_hi = p.kcode[g0 + tp - 4 - q]; ob.id_hi = p.span_id[g0 + tp - 4 - q]; }
+        ObsBatch o;
+        o.sp_lo = o.sp_hi = 1; o.kc_lo = o.kc_hi = 0; o.id_lo = o.id_hi = 0;
+        if (tp - q >= s) { o.kc_lo = p.kcode[g0 + tp - q]; o.id_lo = p.span_id[g0 + tp - q]; }
+        if (tp - 4 - q >= s) { o.kc_hi = p.kcode[g0 + tp - 4 - q]; o.id_hi = p.span_id[g0 + tp - 4 - q]; }
+        return o;
     };
-    if (active) load_batch(top); else { ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0; }
+    ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
+    obn = ob;
+    if (active) { ob = load_batch(top); obn = load_batch(top - 8); }
     int since = 0, done = 0;
 
     for (;;) {
@@ -430,18 +463,17 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
             // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
             const int e = T - 1;
             double wv[NI];
-            if (e == hot) gemv_hot<NS, FRAG>(rF_PT, sF_PT, m.F_PT + (size_t)e * MM, beta, wv, lane);
-            else gemv8<NS, false>(m.F_PT + (size_t)e * MM, beta, wv, lane);
-            if (storing) store_vec(bv, wv, 1.0);
+            double2 pwv[NT];
             {
                 const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double2 v = __ldg(pw + 4 * nt);
-                    wv[2 * nt] *= v.x;
-                    wv[2 * nt + 1] *= v.y;
-                }
+                for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + 4 * nt);
             }
+            if (e == hot) gemv_hot<NS, FRAG>(rF_PT, sF_PT, m.F_PT + (size_t)e * MM, beta, wv, lane);
+            else gemv8<NS, false>(m.F_PT + (size_t)e * MM, beta, wv, lane);
+            if (storing) store_vec(bv, wv, 1.0);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { wv[2 * nt] *= pwv[nt].x; wv[2 * nt + 1] *= pwv[nt].y; }
             if (e == hot) gemv_hot<NS, FRAG>(rF_PinvT, sF_PinvT, m.F_PinvT + (size_t)e * MM, wv, nb, lane);
             else gemv8<NS, false>(m.F_PinvT + (size_t)e * MM, wv, nb, lane);
         } else {
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
             --cur;
             ++done;
             if (cur < s) active = false;
-            else if (top - cur == 8) { top -= 8; load_batch(top); }
+            else if (top - cur == 8) { top -= 8; ob = obn; obn = load_batch(top - 8); }
         } else {
             --since;
         }
