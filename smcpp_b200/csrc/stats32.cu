@@ -26,6 +26,26 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// The state index of an operand row is free to permute (it only permutes the rows / columns of the accumulator), so a
+// lane's four (m-tile) values are the four CONSECUTIVE states 4r..4r+3 -- one 128/256-bit load covering whole lines across
+// the warp -- instead of the textbook 8mt + r.  profiles/r1g: this kernel is bound by L1 wavefronts, not by latency.
+struct dbl4 { double v[4]; };
+__device__ __forceinline__ dbl4 ld4d(const double *p)   // 256-bit read-only load, 32-byte aligned
+{
+    dbl4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+struct flt8 { float v[8]; };
+__device__ __forceinline__ flt8 ld8f(const float *p)
+{
+    flt8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
+}
+
 // sum over the 8 lanes that share q (= over r)
 __device__ __forceinline__ double sum_over_r(double v)
 {
@@ -42,15 +62,15 @@ __device__ __forceinline__ double sum_over_q(double v)
     return v;
 }
 
-// accumulator tile -> shared [32][33] (padded), element (row 8mt + r, col 8nt + 2q + h)
+// accumulator tile -> shared [32][33] (padded): tile (mt, nt) row r is state 4r + mt, its column c is state 4c + nt
 __device__ __forceinline__ void store_acc(double *sm, const double (&acc)[4][4][2], int r, int q)
 {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            sm[(8 * mt + r) * 33 + 8 * nt + 2 * q] = acc[mt][nt][0];
-            sm[(8 * mt + r) * 33 + 8 * nt + 2 * q + 1] = acc[mt][nt][1];
+            sm[(4 * r + mt) * 33 + 4 * (2 * q) + nt] = acc[mt][nt][0];
+            sm[(4 * r + mt) * 33 + 4 * (2 * q + 1) + nt] = acc[mt][nt][1];
         }
 }
 
@@ -103,8 +123,8 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
             for (int nt = 0; nt < 4; ++nt) {
                 const double v = sum_over_q(gacc[nt]);
                 if (q == 0) {
-                    if (first_open) bnd[(warp * 2 + 0) * 32 + 8 * nt + r] = v;       // boundary slot: combined in warp order below
-                    else gs[(size_t)key * 32 + 8 * nt + r] += v;                      // interior key: this warp is its only writer ... so far
+                    if (first_open) bnd[(warp * 2 + 0) * 32 + 4 * r + nt] = v;       // boundary slot: combined in warp order below
+                    else gs[(size_t)key * 32 + 4 * r + nt] += v;                      // interior key: this warp is its only writer ... so far
                 }
                 gacc[nt] = 0.0;
             }
@@ -126,14 +146,12 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
             double pp = 0.0, cn = 1.0;
             if (valid) {
                 const float *ap = alpha_col(b);
-                const double *bv = w.bvec + (size_t)gb * 32;
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ap) + r), c4 = __ldg(reinterpret_cast<const float4 *>(ap + 32) + r);
+                const dbl4 b4 = ld4d(w.bvec + (size_t)gb * 32 + 4 * r), e4 = ld4d(m.E + (size_t)k * 32 + 4 * r);
+                av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+                ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    av[i] = (double)ap[8 * i + r];
-                    ac[i] = (double)ap[32 + 8 * i + r];
-                    be[i] = bv[8 * i + r];
-                    ek[i] = __ldg(m.E + (size_t)k * 32 + 8 * i + r);
-                }
+                for (int i = 0; i < 4; ++i) { be[i] = b4.v[i]; ek[i] = e4.v[i]; }
                 cn = (double)w.cnorm[gb];
             } else {
 #pragma unroll
@@ -179,7 +197,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const double v = sum_over_q(gacc[nt]);
-                    if (q == 0) bnd[(warp * 2 + 1) * 32 + 8 * nt + r] = v;
+                    if (q == 0) bnd[(warp * 2 + 1) * 32 + 4 * r + nt] = v;
                 }
                 if (lane == 0) bkey[warp * 2 + 1] = cur;
             }
@@ -214,19 +232,19 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
         const int l0 = seg[1 + e], l1 = seg[2 + e];
         const int ngrp = (l1 - l0 + 7) >> 3;
         const int gbeg = (int)((long)ngrp * warp / kS32Warps), gend = (int)((long)ngrp * (warp + 1) / kS32Warps);
-        // Pinv_r as A fragments in shared memory: A[a = 8mt + r][i = 4kt + q] at [(mt*8 + kt)*32 + lane]
+        // Pinv_r as A fragments in shared memory (permuted index order, see the header): A[a = 4r + mt][i = 8q + kt]
         {
             const double *Pinv = m.Pinv + (size_t)e * 1024;
             for (int x = tid; x < 1024; x += kS32Warps * 32) {
                 const int ln = x & 31, kt = (x >> 5) & 7, mt = x >> 8;
-                pinv_s[x] = Pinv[(8 * mt + (ln >> 2)) * 32 + 4 * kt + (ln & 3)];
+                pinv_s[x] = Pinv[(4 * (ln >> 2) + mt) * 32 + 8 * (ln & 3) + kt];   // A[a = 4r + mt][i = 8q + kt]
             }
             __syncthreads();
         }
         double invd[4];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-            const double dv = m.dsc[e * 32 + 8 * mt + r];
+            const double dv = m.dsc[e * 32 + 4 * r + mt];
             invd[mt] = dv != 0.0 ? 1.0 / dv : 0.0;
         }
         const double sc = m.scale[e];
@@ -256,10 +274,10 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
             {
                 const bool vr = rB.x >= 0;
                 const int br = vr ? rB.x : 0;
-                const float *ap = alpha_col(br);
+                const flt8 a8 = ld8f(alpha_col(br) + 8 * q);   // states 8q .. 8q+7 of block r
 #pragma unroll
                 for (int kt = 0; kt < 8; ++kt) {
-                    const double bfr = vr ? (double)ap[4 * kt + q] : 0.0;
+                    const double bfr = vr ? (double)a8.v[kt] : 0.0;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) dmma884(u[mt][0], u[mt][1], pinv_s[(mt * 8 + kt) * 32 + lane], bfr);
                 }
@@ -275,10 +293,11 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                 const double *bv = w.bvec + (size_t)gb * 32;
                 const double *pwr = m.pwtab + ((size_t)e * m.n_span + (vb ? rc.y : 0)) * 32;
                 double wv[4], pw[4], dot = 0.0;
+                const dbl4 w4 = ld4d(bv + 4 * r), p4 = ld4d(pwr + 4 * r);   // eigen indices 4r .. 4r+3
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt) {
-                    wv[mt] = vb ? bv[8 * mt + r] : 0.0;
-                    pw[mt] = __ldg(pwr + 8 * mt + r);
+                    wv[mt] = vb ? w4.v[mt] : 0.0;
+                    pw[mt] = p4.v[mt];
                     dot = fma(pw[mt] * u[mt][h], wv[mt], dot);
                 }
                 dot = sum_over_r(dot);
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             const double v = sum_over_q(dacc[mt]);
-            if (q == 0) dred[warp * 32 + 8 * mt + r] = v;
+            if (q == 0) dred[warp * 32 + 4 * r + mt] = v;
         }
         __syncthreads();
         double *Rp = w.Rpart + ((size_t)slab * NE + e) * 1024;
