@@ -144,6 +144,18 @@ int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const 
 int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums,
                      double *reduced);
 
+/*
+ * Full posterior decoding, the `smc++ posterior` variant of the E-step.
+ * Replaces: InferenceManager::saveGamma + the per-block gamma columns of HMM::Estep (reference
+ *           include/inference_manager.h:40, src/hmm.cpp:48-49, 116-121, 134-136, 147-150) and getGammas()
+ *           (src/inference_manager.cpp:136-142).
+ * set_save_gamma(1) makes every following estep() also compute gamma[l][m] for l = 0..L of every contig (column 0 is
+ * alpha_0 o beta_0; a column sums to the block's span); fetch_gamma copies one contig's [(L+1)][M] doubles to the host
+ * (the reference's matrix is M x (L+1); the Python mirror returns the transposed view).
+ */
+int smcpp_b200_set_save_gamma(smcpp_b200_ctx *ctx, int on);
+int smcpp_b200_fetch_gamma(smcpp_b200_ctx *ctx, int contig, double *out /* (L+1)*M */);
+
 /* Diagnostics of the last estep(): see smcpp_b200_stats_t. */
 typedef struct smcpp_b200_stats_t {
     int32_t n_chunks;        /* chunks the contigs were split into */

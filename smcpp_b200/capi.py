@@ -43,7 +43,8 @@ SYMBOLS = [
     "smcpp_b200_host_initial_distribution", "smcpp_b200_host_average_coal_times", "smcpp_b200_host_transition",
     "smcpp_b200_host_emission",
     "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
-    "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat",
+    "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat", "smcpp_b200_set_save_gamma",
+    "smcpp_b200_fetch_gamma",
 ]
 
 
@@ -293,6 +294,16 @@ class Context:
         p = ctypes.c_void_p()
         self._check(lib().smcpp_b200_stream(self._h, ctypes.byref(p)), "stream")
         return p.value or 0
+
+    def set_save_gamma(self, on: bool):
+        self._check(lib().smcpp_b200_set_save_gamma(self._h, ctypes.c_int(1 if on else 0)), "set_save_gamma")
+
+    def fetch_gamma(self, contig: int) -> np.ndarray:
+        """Posterior of one contig as [L+1, M] (the reference holds M x (L+1))."""
+        L = int(self.lengths[contig])
+        out = np.empty((L + 1, self.M))
+        self._check(lib().smcpp_b200_fetch_gamma(self._h, ctypes.c_int(contig), ptr(out, c_f64p)), "fetch_gamma")
+        return out
 
     def debug_alpha_hat(self, contig: int) -> np.ndarray:
         L = int(self.lengths[contig])

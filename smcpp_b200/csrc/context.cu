@@ -91,7 +91,9 @@ struct smcpp_b200_ctx {
     std::vector<uint16_t> h_key;     // packed code: key id | (1 + eigen index) << 11 for span > 1 blocks
     int hot_eig = -1;
     DevBuf<int32_t> d_span, d_span_id, d_span_list;
-    DevBuf<double> m_pwtab;
+    DevBuf<double> m_pwtab, m_invdiff, w_gamma;
+    DevBuf<int64_t> d_gcol_off;
+    bool save_gamma = false, gamma_valid = false;
     DevBuf<uint16_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
@@ -150,7 +152,7 @@ struct smcpp_b200_ctx {
         m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
         m.F_Td = m_F_Td.p; m.F_P = m_F_P.p; m.F_PT = m_F_PT.p; m.F_Pinv = m_F_Pinv.p; m.F_PinvT = m_F_PinvT.p;
         m.Eq = m_Eq.p; m.A32q = m_A32q.p;
-        m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size();
+        m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size(); m.invdiff = m_invdiff.p;
         return m;
     }
     Plan plan() const
@@ -239,7 +241,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     // DevBuf / PinBuf members are released explicitly (they are plain structs without destructors)
-    ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
+    ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
     ctx->d_sl_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
@@ -740,6 +742,20 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     cudaEventRecord(ctx->ev[2], ctx->st);
     launch_stats(m, p, w, ctx->st);
     cudaEventRecord(ctx->ev[3], ctx->st);
+    ctx->gamma_valid = false;
+    if (ctx->save_gamma) {
+        // full posterior decoding (reference saveGamma, src/hmm.cpp:48-49,147-148): M x (L+1) doubles per contig
+        std::vector<int64_t> goff(ctx->C + 1, 0);
+        for (int c = 0; c < ctx->C; ++c) goff[c + 1] = goff[c] + (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
+        CU(ctx->w_gamma.ensure((size_t)goff[ctx->C] * M));
+        CU(ctx->m_invdiff.ensure((size_t)std::max(1, NE) * m.Mp * m.Mp));
+        CU(ctx->d_gcol_off.ensure(ctx->C + 1));
+        CU(cudaMemcpyAsync(ctx->d_gcol_off.p, goff.data(), (ctx->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));   // goff is a stack vector
+        launch_posterior(ctx->model(), p, w, ctx->w_gamma.p, ctx->d_gcol_off.p, ctx->st);
+        ctx->stats.kernel_launches += 2;
+        ctx->gamma_valid = true;
+    }
     launch_finalize(m, p, w, ctx->st);
     cudaEventRecord(ctx->ev[4], ctx->st);
     ctx->stats.kernel_launches += 4;
@@ -887,6 +903,26 @@ int smcpp_b200_copy_reduced_to_device(smcpp_b200_ctx *ctx, void *dst_device, int
     if (count != n) return fail(ctx, "copy_reduced_to_device: count mismatch");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(dst_device, ctx->o_reduced.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int smcpp_b200_set_save_gamma(smcpp_b200_ctx *ctx, int on)
+{
+    if (!ctx) return 1;
+    ctx->save_gamma = on != 0;
+    return 0;
+}
+
+int smcpp_b200_fetch_gamma(smcpp_b200_ctx *ctx, int contig, double *out)
+{
+    if (!ctx || !out || contig < 0 || contig >= ctx->C) return 1;
+    if (!ctx->gamma_valid) return fail(ctx, "fetch_gamma: the last estep() ran without save_gamma");
+    CU(cudaSetDevice(ctx->device));
+    int64_t off = 0;
+    for (int c = 0; c < contig; ++c) off += (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
+    const int64_t cols = (ctx->blk_off[contig + 1] - ctx->blk_off[contig]) + 1;
+    CU(cudaMemcpyAsync(out, ctx->w_gamma.p + (size_t)off * ctx->M, (size_t)cols * ctx->M * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return 0;
 }

@@ -52,6 +52,7 @@ struct Model {
     const double *pwtab;     // [n_eig][n_span][Mp]
     const int32_t *span_list;// [n_span] distinct spans > 1 of the data set
     int n_span;
+    const double *invdiff;   // [n_eig][Mp][Mp] 1/(d~_a - d~_b), built only for posterior decoding
 };
 
 // Static per-dataset layout (set_contigs) + per-plan chunking.
@@ -131,6 +132,7 @@ void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cud
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
+void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
 void launch_fp64_peak(double *sink, int iters, cudaStream_t st);

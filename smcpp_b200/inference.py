@@ -123,9 +123,10 @@ class InferenceManager:
         """Reference: _PyInferenceManager.E_step (smcpp/_smcpp.pyx:185-191) -> InferenceManager::Estep."""
         if self._inputs is None:
             raise RuntimeError("E_step: set_hmm_inputs() has not been called")
-        if self.save_gamma:
-            raise RuntimeError("save_gamma (full posterior decoding) is not part of this path yet")
         pi, T, E, eig = self._inputs
+        for c in self._ctx:
+            if c is not None:
+                c.set_save_gamma(bool(self.save_gamma))
         results = [None] * len(self._ctx)
         errors = []
 
@@ -180,9 +181,18 @@ class InferenceManager:
 
     @property
     def gammas(self):
-        """Reference: _PyInferenceManager.gammas (smcpp/_smcpp.pyx:233-239); without save_gamma only
-        column 0 is defined (src/hmm.cpp:150): returned as [M, 1] per contig."""
-        return [g.reshape(-1, 1).copy() for g in self._need()["gamma0"]]
+        """Reference: _PyInferenceManager.gammas (smcpp/_smcpp.pyx:233-239): per contig an M x (L+1) matrix with
+        save_gamma (the `smc++ posterior` path), else only column 0 (src/hmm.cpp:150), returned as [M, 1]."""
+        o = self._need()
+        if not self.save_gamma:
+            return [g.reshape(-1, 1).copy() for g in o["gamma0"]]
+        ret = [None] * len(self._obs)
+        for ctx, idx in zip(self._ctx, self._shards):
+            if ctx is None:
+                continue
+            for local, glob in enumerate(idx):
+                ret[glob] = ctx.fetch_gamma(local).T
+        return ret
 
     @property
     def gamma_sums(self):

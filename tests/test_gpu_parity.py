@@ -113,17 +113,20 @@ def test_fresh_inputs_against_port(M, n, L):
     w = synth.make_workload("fresh", 2, L, M, n, seed0=900 + M)
     keys = np.unique(np.concatenate([c[:, 1:] for c in w.contigs]), axis=0)
     K = keys.shape[0]
-    # a reversible-ish chain with the reference's uniform mixing, and emissions in (0, 1]
+    # a symmetric doubly stochastic chain (Sinkhorn) with the reference's uniform mixing, so that diag(e) T^T is similar
+    # to a symmetric matrix and every eigensystem is real; emissions in (0, 1]
     base = rng.random((M, M)) ** 4 + np.eye(M) * 50
-    T = base / base.sum(1, keepdims=True)
-    T = (1 - 1e-5) * T + 1e-5 / (M + 1)
+    S = base + base.T
+    for _ in range(200):
+        d = S.sum(1)
+        S = S / np.sqrt(d[:, None] * d[None, :])
+    T = (1 - 1e-5) * S + 1e-5 / (M + 1)
     pi = rng.random(M) + 0.1
     pi /= pi.sum()
     E = np.clip(rng.random((K, M)) * 0.9 + 0.05, 1e-3, 1.0)
     eig_idx = np.array([k for k in range(K) if any(((c[:, 0] > 1) & (c[:, 1:] == keys[k]).all(1)).any() for c in w.contigs)], np.int32)
     eig = capi.host_eigensystems(T, E, eig_idx)
-    if eig["eig_cplx"].any():
-        pytest.skip("random chain has complex eigenvalues")
+    assert not eig["eig_cplx"].any()
     ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
     ctx, out = run_ctx(w.contigs, 1, ref, {"chunk_blocks": 256, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": M % 2})
     for c, obs in enumerate(w.contigs):
@@ -211,3 +214,56 @@ def test_full_size_properties_c2():
     assert np.array_equal(a_gpu, o["alpha_hat"])
     ctx.close()
     ctx2.close()
+
+
+@pytest.mark.parametrize("name,opts", [("c1_2k", {"force_sequential": 1}), ("c2_1500", {"chunk_blocks": 64, "burn_in_blocks": 512}),
+                                       ("c4_twopop_1200", {"chunk_blocks": 128, "burn_in_blocks": 512, "mma_min_chunks": 1}),
+                                       ("m64_600", {"chunk_blocks": 64, "burn_in_blocks": 512, "mma_min_chunks": 1}),
+                                       ("m17_800", {"chunk_blocks": 100, "burn_in_blocks": 512})])
+def test_posterior_decoding_against_port(name, opts):
+    # save_gamma: every column of the posterior (reference src/hmm.cpp:116-121, 134-136, 147-150) against the port,
+    # which is pinned to the reference (tests/test_oracle.py)
+    g = Golden(name)
+    ref = g.ref
+    ctx = capi.Context(0)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    ctx.set_contigs(g.contigs, g.npop, ref["keys"])
+    ctx.set_save_gamma(True)
+    out = ctx.estep(ref["pi"], ref["T"], ref["E"], ref)
+    check_against(out, ref)
+    for c, obs in enumerate(g.contigs):
+        o = port.hmm_estep(obs, ref, save_gamma=True)
+        got = ctx.fetch_gamma(c)
+        assert got.shape == o["gamma_full"].shape
+        assert np.allclose(got[1:].sum(1), obs[:, 0], rtol=1e-9)          # a column sums to the block's span
+        span = np.concatenate([[1], obs[:, 0]])[:, None]
+        # columns compared as distributions.  The reference rounds alpha_hat to float every step (ulp 6e-8): with one
+        # chunk per contig the float trajectory is reproduced bit for bit and the columns agree to fp64 round-off;
+        # chunked runs start each chunk from a burn-in state that equals the reference's to a few float ulps, so a
+        # single column carries that float-level noise (it averages out of the summed statistics, checked above).
+        assert relmax(got / span, o["gamma_full"] / span) <= (1e-10 if opts.get("force_sequential") else 1e-6)
+        # the per-key sums are the column sums of the full posterior (src/hmm.cpp:125-128, 140-143)
+        tot = got[1:].sum(0)
+        assert relmax(tot, out["gamma_sums"][c].sum(0)) <= 1e-9
+    ctx.set_save_gamma(False)
+    ctx.estep(ref["pi"], ref["T"], ref["E"], ref)
+    with pytest.raises(RuntimeError, match="save_gamma"):
+        ctx.fetch_gamma(0)
+    ctx.close()
+
+
+def test_inference_manager_gammas_with_save_gamma():
+    g = Golden("c2_1500")
+    ref = g.ref
+    im = InferenceManager(g.contigs, np.arange(ref["pi"].shape[0] + 1.0), g.npop, keys=ref["keys"])
+    im.set_hmm_inputs(ref["pi"], ref["T"], ref["E"], ref)
+    im.save_gamma = True
+    im.E_step()
+    gam = im.gammas
+    assert len(gam) == len(g.contigs)
+    for c, obs in enumerate(g.contigs):
+        o = port.hmm_estep(obs, ref, save_gamma=True)
+        assert gam[c].shape == (ref["pi"].shape[0], obs.shape[0] + 1)      # M x (L+1), as _PyInferenceManager.gammas
+        span = np.concatenate([[1], obs[:, 0]])[:, None]
+        assert relmax(gam[c].T / span, o["gamma_full"] / span) <= 1e-6
