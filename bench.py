@@ -13,8 +13,8 @@ reference produced for this exact workload; observations are synthetic (smcpp_b2
 
 `value`  : blocks/s with everything resident in HBM (per-step inputs included), wall time of K steps
            bracketed by barrier + synchronize, max over ranks.
-`e2e`    : the same through the host-facing C ABI call (host buffers: per-step inputs H2D, all per-contig
-           results D2H inside the timed region) + the all-reduce.
+`e2e`    : the same through the host-facing C ABI call (host buffers: eigensystems computed by the library, per-step
+           inputs H2D, all per-contig results D2H inside the timed region) + the all-reduce.
 `roofline`: recursion kernels (k_forward || k_backward, the dominant phase) against the measured HBM peak,
            algorithmic bytes of SURVEY 8d; `roofline_fp64` relates the algorithmic flops to the measured
            FP64 FMA peak of this GPU, which is the bound that binds at M = 32.
@@ -208,7 +208,9 @@ def main():
 
     def step_e2e():
         if contigs:
-            o = ctx.estep(model["pi"], model["T"], model["E"], eig)       # H2D inputs, kernels, D2H results
+            # eigensystems computed by the library inside the call (TransitionBundle::update is part of the reference's
+            # Estep, src/inference_manager.cpp:111), then H2D inputs, kernels, D2H results
+            o = ctx.estep(model["pi"], model["T"], model["E"], None)
             host_out.update(o)
             red.copy_(torch.from_numpy(o["reduced"]))
         else:

@@ -54,7 +54,7 @@ def build(force: bool = False) -> str:
     newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src))
     newest = max(newest, os.path.getmtime(os.path.join(_HERE, "..", "include", "smcpp_b200.h")))
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
-        subprocess.check_call(["make", "-s", "-C", src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-s", "-j", "8", "-C", src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return LIB_PATH
 
 

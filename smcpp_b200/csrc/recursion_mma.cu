@@ -100,6 +100,37 @@ __device__ __forceinline__ float8 ldg256(const float *p)
     return r;
 }
 
+// ---- packed float pairs (sm_100 FFMA2): the span-1 float GEMV must round the product and the sum separately (the
+// reference's Eigen GEMV is compiled without FMA), which costs an FMUL and an FADD per element.  Two exact identities
+// let one packed instruction do each for TWO elements without ever fusing them:
+//     fl(x a)   = fma.rn(x, a, -0.0)      (adding -0 changes neither the value nor the sign of a zero product)
+//     fl(p + y) = fma.rn(p, 1.0, y)
+// (ptxas contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 even under --fmad=false, so the plain packed
+// mul / add forms cannot be used here.)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+constexpr f32x2 kNegZero2 = 0x8000000080000000ull, kOne2 = 0x3f8000003f800000ull;
+struct f32x2x4 { f32x2 v[4]; };
+// one 256-bit read-only load of 8 consecutive floats as 4 packed pairs, 32-byte aligned
+__device__ __forceinline__ f32x2x4 ldg256p(const float *p)
+{
+    f32x2x4 r;
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+    return r;
+}
+
 // Eigen's float sum() order for exactly MPX = 32 NS aligned coefficients in shared memory (see eigen_sum_f32), unrolled
 template <int MPX>
 __device__ __forceinline__ float eigen_sum_f32_full(const float *v)
@@ -305,24 +336,29 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             __syncwarp();
             const float4 *xr = reinterpret_cast<const float4 *>(xs);
             const float *A = m.A32q + ((size_t)k * MP * 4 + q) * NI;   // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
-            float y[NI];
+            f32x2 y2[NI / 2];
 #pragma unroll
-            for (int idx = 0; idx < NI; ++idx) y[idx] = 0.f;
+            for (int idx = 0; idx < NI / 2; ++idx) y2[idx] = 0ull;
 #pragma unroll(NS == 1 ? 8 : 2)
             for (int i4 = 0; i4 < MP / 4; ++i4) {
                 const float4 xv = xr[i4];
 #pragma unroll
                 for (int cidx = 0; cidx < 4; ++cidx) {
                     const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
+                    const f32x2 xx = pack2(xi, xi);
                     const float *Ai = A + (size_t)(4 * i4 + cidx) * 4 * NI;
 #pragma unroll
                     for (int h = 0; h < NS; ++h) {
-                        const float8 av = ldg256(Ai + 8 * h);
+                        const f32x2x4 av = ldg256p(Ai + 8 * h);
 #pragma unroll
-                        for (int j8 = 0; j8 < 8; ++j8) y[8 * h + j8] = __fadd_rn(y[8 * h + j8], __fmul_rn(xi, av.v[j8]));
+                        for (int j2 = 0; j2 < 4; ++j2)   // y = fl(y + fl(x_i a_ij)), two columns per instruction
+                            y2[4 * h + j2] = fma2(fma2(xx, av.v[j2], kNegZero2), kOne2, y2[4 * h + j2]);
                     }
                 }
             }
+            float y[NI];
+#pragma unroll
+            for (int idx = 0; idx < NI / 2; ++idx) unpack2(y2[idx], y[2 * idx], y[2 * idx + 1]);
             __syncwarp();
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
