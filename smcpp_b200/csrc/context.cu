@@ -90,16 +90,19 @@ struct smcpp_b200_ctx {
     std::vector<int32_t> h_span, h_span_id, span_list;
     std::vector<uint16_t> h_key;     // packed code: key id | (1 + eigen index) << 11 for span > 1 blocks
     int hot_eig = -1;
+    int hot_keys[4] = {-1, -1, -1, -1};   // most frequent span-1 keys (the forward kernel keeps their step matrices in shared memory)
     DevBuf<int32_t> d_span, d_span_id, d_span_list;
-    DevBuf<double> m_pwtab, m_invdiff, w_gamma;
+    DevBuf<double> m_pwtab, m_pwq, m_invdiff, w_gamma;
     DevBuf<int64_t> d_gcol_off;
     bool save_gamma = false, gamma_valid = false;
     DevBuf<uint16_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
     DevBuf<uint32_t> d_sl_mask;
-    DevBuf<int2> d_srec;
-    DevBuf<int32_t> d_seg;
+    DevBuf<int2> d_srec, d_erec;
+    DevBuf<int32_t> d_seg, d_it_len, d_it_contig, d_it_eig, d_it_off;
+    DevBuf<int64_t> d_it_start;
+    int n_items = 0;
     DevBuf<int> d_eig_of_key, d_key_of_eig;
 
     // ---- options
@@ -132,6 +135,7 @@ struct smcpp_b200_ctx {
     DevBuf<double> m_F_Td, m_F_P, m_F_PT, m_F_Pinv, m_F_PinvT, m_Eq;
     bool use_mma = false;
     DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
+    DevBuf<double> w_uvec, w_Ritem, w_ditem;
     DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
         w_scratch, w_sums, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
     DevBuf<uint8_t> w_fwd_flag, w_bwd_flag;
@@ -152,6 +156,9 @@ struct smcpp_b200_ctx {
         m.dsc = m_dsc.p; m.logd = m_logd.p; m.dr = m_dr.p; m.scale = m_scale.p; m.logscale = m_logscale.p;
         m.F_Td = m_F_Td.p; m.F_P = m_F_P.p; m.F_PT = m_F_PT.p; m.F_Pinv = m_F_Pinv.p; m.F_PinvT = m_F_PinvT.p;
         m.Eq = m_Eq.p; m.A32q = m_A32q.p;
+        m.pwq = m_pwq.p;
+        m.c_negzero2 = 0x8000000080000000ull; m.c_one2 = 0x3f8000003f800000ull;
+        for (int i = 0; i < 4; ++i) m.hot_keys[i] = hot_keys[i];
         m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size(); m.invdiff = m_invdiff.p;
         return m;
     }
@@ -166,12 +173,14 @@ struct smcpp_b200_ctx {
         p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
         p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
         p.srec = d_srec.p; p.seg = d_seg.p;
+        p.n_items = n_items; p.erec = d_erec.p; p.it_start = d_it_start.p; p.it_len = d_it_len.p; p.it_contig = d_it_contig.p;
+        p.it_eig = d_it_eig.p; p.it_off = d_it_off.p;
         return p;
     }
     Work work() const
     {
         Work w;
-        w.alpha = w_alpha.p; w.cnorm = w_cnorm.p; w.bvec = w_bvec.p;
+        w.alpha = w_alpha.p; w.cnorm = w_cnorm.p; w.bvec = w_bvec.p; w.uvec = w_uvec.p; w.Ritem = w_Ritem.p; w.ditem = w_ditem.p;
         w.start_used = w_start_used.p; w.end_alpha = w_end_alpha.p; w.end_alpha_prev = w_end_alpha_prev.p;
         w.ll_chunk = w_ll_chunk.p; w.bstart_used = w_bstart_used.p; w.beta_out = w_beta_out.p;
         w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p;
@@ -241,10 +250,11 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     // DevBuf / PinBuf members are released explicitly (they are plain structs without destructors)
-    ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
+    ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_pwq.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
+    ctx->d_sl_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
+    ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
@@ -282,6 +292,8 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
     else if (n == "force_mma_forward") ctx->opt_force_mma_forward = value != 0;
     else if (n == "mma_min_chunks") ctx->opt_mma_min_chunks = std::max(1, (int)value);
+    else if (n == "chunks_per_warp") smcb::set_chunks_per_warp((int)value);   // process-wide, 0 = automatic
+    else if (n == "fwd_cached_keys") smcb::set_fwd_cached_keys((int)value);   // process-wide (sizes the kernel's shared memory)
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;
@@ -374,7 +386,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     ctx->span_list.clear();
     std::unordered_map<int32_t, int32_t> span_index;
     ctx->present.assign((size_t)n_contigs * K, 0);
-    std::vector<int64_t> eig_count(std::max(1, ctx->n_eig), 0);
+    std::vector<int64_t> eig_count(std::max(1, ctx->n_eig), 0), site_count(K, 0);
     for (int c = 0; c < n_contigs; ++c) {
         const int32_t *o = obs[c];
         KeyRow last{};
@@ -400,12 +412,19 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
             }
             ctx->h_key[g0 + l] = (uint16_t)(last_id | ((e + 1) << 11));
             if (e >= 0) ++eig_count[e];
+            if (row[0] == 1) ++site_count[last_id];
             ctx->present[(size_t)c * K + last_id] = 1;
         }
     }
     ctx->hot_eig = -1;
     for (int e = 0; e < ctx->n_eig; ++e)
         if (ctx->hot_eig < 0 || eig_count[e] > eig_count[ctx->hot_eig]) ctx->hot_eig = e;
+    {
+        std::vector<int> order(K);
+        for (int k = 0; k < K; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return site_count[a] > site_count[b]; });
+        for (int i = 0; i < 4; ++i) ctx->hot_keys[i] = (i < K && site_count[order[i]] > 0) ? order[i] : -1;
+    }
     CU(ctx->d_span.ensure(ctx->total));
     CU(ctx->d_key.ensure(ctx->total));
     CU(cudaMemcpy(ctx->d_span.p, ctx->h_span.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -547,6 +566,49 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         }
         ctx->slab_off[c + 1] = (int)sl_contig.size();
     }
+    // M <= 32: span>1 statistics items -- per (contig, eigen key) the blocks in span-id order (counting sort, block order
+    // kept within a span), cut into items of kItemBlocks
+    std::vector<int2> erec;
+    std::vector<int64_t> it_start;
+    std::vector<int32_t> it_len, it_contig, it_eig, it_off;
+    if (Mp == 32 && NEp > 0) {
+        const int NS = (int)ctx->span_list.size();
+        std::vector<int64_t> cnt;
+        for (int c = 0; c < C; ++c) {
+            const int64_t g0 = ctx->blk_off[c], L = ctx->blk_off[c + 1] - g0;
+            // one counting sort over (eigen key, span id)
+            cnt.assign((size_t)NEp * NS + 1, 0);
+            for (int64_t b = 0; b < L; ++b) {
+                const int cls = ctx->h_key[g0 + b] >> 11;
+                if (cls) ++cnt[(size_t)(cls - 1) * NS + ctx->h_span_id[g0 + b] + 1];
+            }
+            for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+            const size_t base = erec.size();
+            erec.resize(base + (size_t)cnt.back());
+            for (int64_t b = 0; b < L; ++b) {
+                const int cls = ctx->h_key[g0 + b] >> 11;
+                if (cls) {
+                    const int sid = ctx->h_span_id[g0 + b];
+                    erec[base + (size_t)cnt[(size_t)(cls - 1) * NS + sid]++] = make_int2((int)b, sid);
+                }
+            }
+            // after the scatter cnt[(e, sid)] is the END of that bucket; eigen key e spans [end of e-1, end of e)
+            int64_t lo = 0;
+            for (int e = 0; e < NEp; ++e) {
+                const int64_t hi = cnt[(size_t)e * NS + NS - 1];
+                it_off.push_back((int32_t)it_len.size());
+                for (int64_t a = lo; a < hi; a += kItemBlocks) {
+                    it_start.push_back((int64_t)base + a);
+                    it_len.push_back((int32_t)std::min<int64_t>(kItemBlocks, hi - a));
+                    it_contig.push_back(c);
+                    it_eig.push_back(e);
+                }
+                lo = hi;
+            }
+        }
+        it_off.push_back((int32_t)it_len.size());
+    }
+    ctx->n_items = (int)it_len.size();
     ctx->n_chunks = (int)ch_contig.size();
     ctx->n_slabs = (int)sl_contig.size();
     ctx->n_cols = cols;
@@ -569,6 +631,14 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     UP(d_sl_mask, sl_mask);
     UP(d_srec, srec);
     UP(d_seg, seg);
+    if (ctx->n_items) {
+        UP(d_erec, erec);
+        UP(d_it_start, it_start);
+        UP(d_it_len, it_len);
+        UP(d_it_contig, it_contig);
+        UP(d_it_eig, it_eig);
+        UP(d_it_off, it_off);
+    }
 #undef UP
     const int K = ctx->K, NE = std::max(1, ctx->n_eig);
     const size_t MM = (size_t)Mp * Mp;
@@ -587,6 +657,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->m_scale.ensure(NE));
     CU(ctx->m_logscale.ensure(NE));
     CU(ctx->m_pwtab.ensure((size_t)NE * ctx->span_list.size() * Mp));
+    CU(ctx->m_pwq.ensure((size_t)NE * ctx->span_list.size() * Mp));
     if (Mp == 32 || Mp == 64 || Mp == 128) {
         CU(ctx->m_A32q.ensure((size_t)K * MM));
         CU(ctx->m_F_Td.ensure(MM));
@@ -599,6 +670,11 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->w_alpha.ensure((size_t)cols * Mp));
     CU(ctx->w_cnorm.ensure(ctx->total));
     CU(ctx->w_bvec.ensure((size_t)ctx->total * Mp));
+    if (Mp == 32) {
+        CU(ctx->w_uvec.ensure((size_t)ctx->total * 32));
+        CU(ctx->w_Ritem.ensure((size_t)std::max(1, ctx->n_items) * 1024));
+        CU(ctx->w_ditem.ensure((size_t)std::max(1, ctx->n_items) * 32));
+    }
     CU(ctx->w_start_used.ensure((size_t)ctx->n_chunks * Mp));
     CU(ctx->w_end_alpha.ensure((size_t)ctx->n_chunks * Mp));
     CU(ctx->w_end_alpha_prev.ensure((size_t)ctx->n_chunks * Mp));

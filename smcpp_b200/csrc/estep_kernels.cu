@@ -653,8 +653,20 @@ __global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w
     else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 2u << (int)(y / Mp); }
     else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 1u; }
     double acc = 0.0;
-    for (int s = sl0; s < sl1; ++s)
-        if (p.sl_mask[s] & bit) acc += src[(size_t)s * sstride];
+    if (Mp == 32 && x >= oR && x < oG) {
+        // M <= 32: R_e / D_e partials come per work item of k_stats32e (fixed order: bitwise reproducible)
+        const bool isR = x < oD;
+        const size_t y = isR ? x - oR : x - oD;
+        const int e = (int)(isR ? y / MM : y / Mp);
+        const size_t off = isR ? y % MM : y % Mp;
+        if (p.n_items > 0) {
+            const int i0 = p.it_off[t * NE + e], i1 = p.it_off[t * NE + e + 1];
+            for (int i = i0; i < i1; ++i) acc += isR ? w.Ritem[(size_t)i * MM + off] : w.ditem[(size_t)i * Mp + off];
+        }
+    } else {
+        for (int s = sl0; s < sl1; ++s)
+            if (p.sl_mask[s] & bit) acc += src[(size_t)s * sstride];
+    }
     w.sums[(size_t)t * stride + x] = acc;
 }
 
@@ -775,11 +787,15 @@ __global__ void k_setup_pwtab(Model m)
     const int Mp = m.Mp;
     const long n = (long)m.n_eig * m.n_span * Mp;
     double *tab = const_cast<double *>(m.pwtab);
+    double *tabq = (Mp == 32 || Mp == 64 || Mp == 128) ? const_cast<double *>(m.pwq) : nullptr;
     for (long x = blockIdx.x * (long)blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) {
         const int a = (int)(x % Mp);
         const long es = x / Mp;
         const int sid = (int)(es % m.n_span), e = (int)(es / m.n_span);
-        tab[x] = pow_span(m.dsc[(size_t)e * Mp + a], m.logd[(size_t)e * Mp + a], m.span_list[sid]);
+        const double v = pow_span(m.dsc[(size_t)e * Mp + a], m.logd[(size_t)e * Mp + a], m.span_list[sid]);
+        tab[x] = v;
+        // tensor-path copy, q-major: state a = 8g + 2q + h sits at q * (Mp / 4) + 2g + h  (recursion_mma.cu: st_of)
+        if (tabq) tabq[es * Mp + ((a >> 1) & 3) * (Mp / 4) + 2 * (a >> 3) + (a & 1)] = v;
     }
 }
 

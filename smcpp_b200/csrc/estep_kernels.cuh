@@ -50,6 +50,9 @@ struct Model {
     // d~^span tables: one row per (eigen key, distinct span) -- the reference tabulates per (span, key) too
     // (span_Qs, src/transition_bundle.cpp:29-58); rows are built per E-step by k_setup_pwtab
     const double *pwtab;     // [n_eig][n_span][Mp]
+    const double *pwq;       // the same rows in the tensor path's per-lane state order: pwq[q*(Mp/4) + idx] = pw[st(q, idx)]
+    int hot_keys[4];         // most frequent span-1 keys of the data set (descending), -1 = none
+    unsigned long long c_negzero2, c_one2;   // packed float pairs {-0.0f, -0.0f} and {1.0f, 1.0f}, see recursion_mma.cu (pack2)
     const int32_t *span_list;// [n_span] distinct spans > 1 of the data set
     int n_span;
     const double *invdiff;   // [n_eig][Mp][Mp] 1/(d~_a - d~_b), built only for posterior decoding
@@ -81,6 +84,16 @@ struct Plan {
     // processing order of the statistics kernel: per slab [span-1 blocks sorted by key | eigen key 0 | eigen key 1 ...]
     const int2 *srec;        // [total]  (block index within the contig, key id for span-1 blocks / span id otherwise), at the slab's own offset
     const int32_t *seg;      // [n_slabs][n_eig + 2] segment boundaries (relative to the slab start)
+    // M <= 32: work items of the span>1 statistics kernel (stats32.cu: k_stats32e).  The span>1 blocks of each
+    // (contig, eigen key) are sorted by span id -- blocks of equal span share d~^span, so a whole run needs ONE
+    // rank-1 accumulation plus one weighting per run instead of a rank-2 update per block -- and cut into items.
+    int n_items;
+    const int2 *erec;        // [#span>1 blocks]  (block index within the contig, span id), item after item
+    const int64_t *it_start; // [n_items] first entry of the item in erec
+    const int32_t *it_len;   // [n_items]
+    const int32_t *it_contig;// [n_items]
+    const int32_t *it_eig;   // [n_items]
+    const int32_t *it_off;   // [C * n_eig + 1] first item of (contig, eigen key)
 };
 
 // Work buffers.
@@ -88,6 +101,9 @@ struct Work {
     float *alpha;            // [n_cols][Mp]  chunk-local alpha_hat columns (column 0 of a chunk = its start)
     float *cnorm;            // [total]       float forward normaliser of span-1 blocks (hmm.cpp:87)
     double *bvec;            // [total][Mp]   beta_l (span 1) or w_l = P_r^T beta_l (span > 1)
+    double *uvec;            // [total][32]   M <= 32: u_l = Pinv_r alpha_hat_{l-1} of span>1 blocks, written by the forward pass
+    double *Ritem;           // [n_items][32*32]  per-item partials of R_e (M <= 32)
+    double *ditem;           // [n_items][32]     per-item partials of D_e
     float *start_used;       // [n_chunks][Mp]
     float *end_alpha;        // [n_chunks][Mp]
     float *end_alpha_prev;   // [n_chunks][Mp] snapshot of the previous sweep
@@ -121,11 +137,14 @@ void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, c
 size_t sums_stride(const Model &m);
 int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
+constexpr int kItemBlocks = 4096;   // span>1 blocks per work item of k_stats32e
 void launch_setup_pwtab(const Model &m, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
 void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp in {32, 64, 128}, pass 0, <= 8 chunks / warp
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);
 int resident_warps_mma(int n_sm, int Mp);
+void set_fwd_cached_keys(int n);
+void set_chunks_per_warp(int g);
 bool mma_forward_pays(int n_chunks, int n_sm, int Mp);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);

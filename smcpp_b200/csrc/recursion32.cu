@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_forward32(Model m, Plan p, Wo
                     pw = pow_span(m.dsc[e * 32 + lane], m.logd[e * 32 + lane], span);
                     lsc = m.logscale[e];
                 }
+                if (b >= s) w.uvec[(size_t)(g0 + b) * 32 + lane] = u;   // operand of the statistics pass (stats32.cu)
                 __syncwarp();
                 xd[lane] = pw * u;
                 __syncwarp();

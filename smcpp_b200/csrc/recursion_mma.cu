@@ -105,8 +105,10 @@ __device__ __forceinline__ float8 ldg256(const float *p)
 // let one packed instruction do each for TWO elements without ever fusing them:
 //     fl(x a)   = fma.rn(x, a, -0.0)      (adding -0 changes neither the value nor the sign of a zero product)
 //     fl(p + y) = fma.rn(p, 1.0, y)
-// (ptxas contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 even under --fmad=false, so the plain packed
-// mul / add forms cannot be used here.)
+// ptxas (12.9) contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into ONE fused FFMA2 even under --fmad=false, and it
+// does the same to the two fma forms above when -0.0 and 1.0 are literals (it first simplifies them to mul / add).  The
+// two constants therefore arrive as kernel parameters (Model::c_negzero2 / c_one2), which ptxas cannot see through; the
+// SASS then holds exactly two FFMA2 per element pair (checked with cuobjdump, and bit for bit by the parity tests).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
@@ -121,7 +123,6 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-constexpr f32x2 kNegZero2 = 0x8000000080000000ull, kOne2 = 0x3f8000003f800000ull;
 struct f32x2x4 { f32x2 v[4]; };
 // one 256-bit read-only load of 8 consecutive floats as 4 packed pairs, 32-byte aligned
 __device__ __forceinline__ f32x2x4 ldg256p(const float *p)
@@ -129,6 +130,41 @@ __device__ __forceinline__ f32x2x4 ldg256p(const float *p)
     f32x2x4 r;
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ void lds2p(const float *p, f32x2 &a, f32x2 &b)   // 128-bit shared load of 4 floats as 2 packed pairs
+{
+    asm("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"((unsigned)__cvta_generic_to_shared(p)));
+}
+
+// y[j] = fl(y[j] + fl(x_i A(i, j))) for i = 0..MP-1 in order, for this lane's 8 NS columns (packed in pairs):
+// the reference's k-sequential axpy order with the float-rounded step matrix (src/hmm.cpp:85-89).
+// A points at this lane's columns of row 0 (row stride 4 NI floats), in global memory (read-only path) or, for the
+// frequent span-1 keys, in shared memory (kSm): ncu r1g showed the global variant parked on the long scoreboard for
+// ~200 cycles per 4 rows -- the step matrices of 60+ keys do not stay in L1 next to the streaming alpha / beta traffic.
+template <int NS, bool kSm>
+__device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32x2 (&y2)[4 * NS], f32x2 kNegZero2, f32x2 kOne2)
+{
+    constexpr int MP = 32 * NS, NI = 8 * NS;
+#pragma unroll(NS == 1 ? 8 : 2)
+    for (int i4 = 0; i4 < MP / 4; ++i4) {
+        const float4 xv = xr[i4];
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
+            const f32x2 xx = pack2(xi, xi);
+            const float *Ai = A + (size_t)(4 * i4 + cidx) * 4 * NI;
+#pragma unroll
+            for (int h = 0; h < NS; ++h) {
+                f32x2x4 av;
+                if (kSm) { lds2p(Ai + 8 * h, av.v[0], av.v[1]); lds2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
+                else av = ldg256p(Ai + 8 * h);
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2)   // two columns per instruction
+                    y2[4 * h + j2] = fma2(fma2(xx, av.v[j2], kNegZero2), kOne2, y2[4 * h + j2]);
+            }
+        }
+    }
 }
 
 // Eigen's float sum() order for exactly MPX = 32 NS aligned coefficients in shared memory (see eigen_sum_f32), unrolled
@@ -213,7 +249,7 @@ struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of t
 // forward and backward then run one after the other), shared memory (all warps of both kernels resident at once) or
 // global memory through the read-only path (M = 128: a fragment table is 128 KB).  The launcher picks.
 template <int NS, int FRAG>
-__global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G)
+__global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G, int nkc)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP, XS = MP + 4;
     constexpr int NF = FRAG == kFragReg ? 32 : 1;
@@ -244,6 +280,14 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
         }
     }
     float *xs = s_x + ((size_t)warp * 8 + n) * XS;   // this chunk's row (stride XS floats: fewer bank conflicts)
+    // float step matrices of the nkc most frequent span-1 keys, [nkc][MM] in A32q order
+    float *s_A = s_x + (size_t)kMW * 8 * XS;
+    for (int sl = 0; sl < nkc; ++sl) {
+        const float4 *src = reinterpret_cast<const float4 *>(m.A32q + (size_t)m.hot_keys[sl] * MM);
+        float4 *dst = reinterpret_cast<float4 *>(s_A + (size_t)sl * MM);
+        for (int x4 = tid; x4 < MM / 4; x4 += kMW * 32) dst[x4] = __ldg(src + x4);
+    }
+    if (nkc > 0) __syncthreads();
     const int M = m.M;
 
     // G (<= 8) chunks per warp: small inputs spread over more warps (rows n >= G of the MMA stay idle)
@@ -268,34 +312,52 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 
     int base = cur;
     ObsBatch ob, obn;                         // current batch of 8 blocks and the one after it (fetched a batch ahead)
+    // Loads are unconditional with a clamped index: a guarded load with a default value costs a select right behind the
+    // load, which parks the warp on the scoreboard where the batch is fetched (ncu r1g: 3-5 % of the kernel).  Entries
+    // past the chunk's end are never used (the chunk goes inactive first); idle lanes read chunk 0's rows.
     auto load_batch = [&](int b) {
         ObsBatch o;
-        o.sp_lo = o.sp_hi = 1; o.kc_lo = o.kc_hi = 0; o.id_lo = o.id_hi = 0;
-        if (b + q < bend) { o.sp_lo = p.span[g0 + b + q]; o.kc_lo = p.kcode[g0 + b + q]; o.id_lo = p.span_id[g0 + b + q]; }
-        if (b + 4 + q < bend) { o.sp_hi = p.span[g0 + b + 4 + q]; o.kc_hi = p.kcode[g0 + b + 4 + q]; o.id_hi = p.span_id[g0 + b + 4 + q]; }
+        const int64_t i0 = g0 + min(b + q, bend - 1), i1 = g0 + min(b + 4 + q, bend - 1);
+        o.sp_lo = p.span[i0]; o.kc_lo = p.kcode[i0]; o.id_lo = p.span_id[i0];
+        o.sp_hi = p.span[i1]; o.kc_hi = p.kcode[i1]; o.id_hi = p.span_id[i1];
         return o;
     };
-    ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
-    obn = ob;
-    if (active) { ob = load_batch(base); obn = load_batch(base + 8); }
+    ob = load_batch(base);
+    obn = load_batch(base + 8);
     double llsum = 0.0, lprod = 1.0;
     int lcnt = 0, done = 0, rounds = 0;
+    // (span, code, span id) of the chunk's current block and, for a span>1 block, its d~^span vector: fetched at the END
+    // of the previous round, so the table row's L2 latency hides behind the round bookkeeping and the first GEMV
+    // (ptxas sinks a load issued inside the round down to its first use).
+    int span, kc, sid;
+    auto fetch_cur = [&]() {
+        const int pos = cur - base;
+        const int src = (lane & ~3) | (pos & 3);
+        span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
+        kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
+    };
+    double2 pwv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) pwv[nt] = make_double2(0.0, 0.0);
+    auto load_pw = [&]() {   // states st(q, 2nt), st(q, 2nt + 1) of the q-major table
+        const double2 *pw = reinterpret_cast<const double2 *>(m.pwq + ((size_t)((kc >> 11) - 1) * m.n_span + sid) * MP + q * NI);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + nt);
+    };
+    fetch_cur();
+    if (active && (kc >> 11) > 0) load_pw();
 
     for (;;) {
         const unsigned am = __ballot_sync(kAll, active);
         if (!am) break;
         ++rounds;
-        const int pos = cur - base;
-        const int src = (lane & ~3) | (pos & 3);
-        const int span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
-        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
-        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
         const int type = active ? (kc >> 11) : -1;
         // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
         const int T = __shfl_sync(kAll, type, lead & 31);
         const bool adv = active && type == T;
-        const int k = adv ? (kc & 2047) : 0;
+        const int k = adv ? (kc & 2047) : (nkc > 0 ? m.hot_keys[0] : 0);
         float xn[NI];
         double cmul = 1.0, cadd = 0.0;
         float sf = 0.f;
@@ -303,18 +365,19 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             // a = P_r (d~^span o (Pinv_r alpha_prev)); reference src/hmm.cpp:74-80
             const int e = T - 1;
             double xd[NI], u[NI], a[NI];
-            // d~^span from the per-E-step table (states 8nt + 2q, 8nt + 2q + 1 are adjacent); issued before the first GEMV
-            double2 pwv[NT];
-            {
-                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + 4 * nt);
-            }
 #pragma unroll
             for (int idx = 0; idx < NI; ++idx) xd[idx] = (double)x[idx];
             if (e == hot) gemv_hot<NS, FRAG>(rF_Pinv, sF_Pinv, m.F_Pinv + (size_t)e * MM, xd, u, lane);
             else gemv8<NS, false>(m.F_Pinv + (size_t)e * MM, xd, u, lane);
             const int sp = adv ? span : 1;
+            if constexpr (NS == 1) {
+                // u_l = Pinv_r alpha_hat_{l-1} is an operand of the statistics pass (stats32.cu), stored in eigen-index order
+                if (adv && cur >= s) {
+                    double *ud = w.uvec + (size_t)(g0 + cur) * 32 + 2 * q;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<double2 *>(ud + 8 * nt) = make_double2(u[2 * nt], u[2 * nt + 1]);
+                }
+            }
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { u[2 * nt] *= pwv[nt].x; u[2 * nt + 1] *= pwv[nt].y; }
             if (e == hot) gemv_hot<NS, FRAG>(rF_P, sF_P, m.F_P + (size_t)e * MM, u, a, lane);
@@ -335,26 +398,17 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(x[2 * nt], x[2 * nt + 1]);
             __syncwarp();
             const float4 *xr = reinterpret_cast<const float4 *>(xs);
-            const float *A = m.A32q + ((size_t)k * MP * 4 + q) * NI;   // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
             f32x2 y2[NI / 2];
 #pragma unroll
             for (int idx = 0; idx < NI / 2; ++idx) y2[idx] = 0ull;
-#pragma unroll(NS == 1 ? 8 : 2)
-            for (int i4 = 0; i4 < MP / 4; ++i4) {
-                const float4 xv = xr[i4];
-#pragma unroll
-                for (int cidx = 0; cidx < 4; ++cidx) {
-                    const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
-                    const f32x2 xx = pack2(xi, xi);
-                    const float *Ai = A + (size_t)(4 * i4 + cidx) * 4 * NI;
-#pragma unroll
-                    for (int h = 0; h < NS; ++h) {
-                        const f32x2x4 av = ldg256p(Ai + 8 * h);
-#pragma unroll
-                        for (int j2 = 0; j2 < 4; ++j2)   // y = fl(y + fl(x_i a_ij)), two columns per instruction
-                            y2[4 * h + j2] = fma2(fma2(xx, av.v[j2], kNegZero2), kOne2, y2[4 * h + j2]);
-                    }
-                }
+            int slot = -1;
+            for (int sl = 0; sl < nkc; ++sl)
+                if (k == m.hot_keys[sl]) slot = sl;
+            if (nkc > 0 && __all_sync(kAll, slot >= 0)) {
+                float_gemv<NS, true>(s_A + (size_t)slot * MM + q * NI, xr, y2, m.c_negzero2, m.c_one2);
+            } else {
+                // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
+                float_gemv<NS, false>(m.A32q + ((size_t)k * MP * 4 + q) * NI, xr, y2, m.c_negzero2, m.c_one2);
             }
             float y[NI];
 #pragma unroll
@@ -390,6 +444,8 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             if (cur >= bend) active = false;
             else if (cur - base == 8) { base += 8; ob = obn; obn = load_batch(base + 8); }
         }
+        fetch_cur();
+        if (adv && active && (kc >> 11) > 0) load_pw();
     }
     if (c < p.n_chunks) {
         store_col(w.end_alpha + (size_t)c * MP);
@@ -454,30 +510,46 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
 
     int top = cur;                            // batch = blocks top, top-1, ..., top-7; lane q holds top-q and top-4-q
     ObsBatch ob, obn;
-    auto load_batch = [&](int tp) {
+    auto load_batch = [&](int tp) {   // unconditional, clamped (see the forward kernel)
         ObsBatch o;
-        o.sp_lo = o.sp_hi = 1; o.kc_lo = o.kc_hi = 0; o.id_lo = o.id_hi = 0;
-        if (tp - q >= s) { o.kc_lo = p.kcode[g0 + tp - q]; o.id_lo = p.span_id[g0 + tp - q]; }
-        if (tp - 4 - q >= s) { o.kc_hi = p.kcode[g0 + tp - 4 - q]; o.id_hi = p.span_id[g0 + tp - 4 - q]; }
+        const int64_t i0 = g0 + max(tp - q, s), i1 = g0 + max(tp - 4 - q, s);
+        o.sp_lo = o.sp_hi = 1;
+        o.kc_lo = p.kcode[i0]; o.id_lo = p.span_id[i0];
+        o.kc_hi = p.kcode[i1]; o.id_hi = p.span_id[i1];
         return o;
     };
-    ob.sp_lo = ob.sp_hi = 1; ob.kc_lo = ob.kc_hi = 0; ob.id_lo = ob.id_hi = 0;
-    obn = ob;
-    if (active) { ob = load_batch(top); obn = load_batch(top - 8); }
+    ob = load_batch(top);
+    obn = load_batch(top - 8);
     int since = 0, done = 0;
+    // code and span id of the chunk's current block and the vector that multiplies inside its step -- d~^span (span > 1)
+    // or e_k (span 1), both q-major -- fetched at the END of the previous round (see the forward kernel)
+    int kc, sid;
+    auto fetch_cur = [&]() {
+        const int pos = top - cur;
+        const int src = (lane & ~3) | (pos & 3);
+        kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
+    };
+    double2 opv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) opv[nt] = make_double2(0.0, 0.0);
+    auto load_op = [&]() {
+        const int ty = kc >> 11;
+        const double *row = ty > 0 ? m.pwq + ((size_t)(ty - 1) * m.n_span + sid) * MP : m.Eq + (size_t)(kc & 2047) * MP;
+        const double2 *src = reinterpret_cast<const double2 *>(row + q * NI);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) opv[nt] = __ldg(src + nt);
+    };
+    fetch_cur();
+    if (active) load_op();
 
     for (;;) {
         const unsigned am = __ballot_sync(kAll, active);
         if (!am) break;
-        const int pos = top - cur;
-        const int src = (lane & ~3) | (pos & 3);
-        const int kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
-        const int sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
         const int type = active ? (kc >> 11) : -1;
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
         const int T = __shfl_sync(kAll, type, lead & 31);
         const bool adv = active && type == T;
-        const int k = adv ? (kc & 2047) : 0;
         // the chunk's verified start value: normalised, recorded before the first stored step
         const bool rec = adv && cur == bend - 1;
         if (__any_sync(kAll, rec)) {
@@ -499,29 +571,21 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
             // beta <- Pinv_r^T (d~^span o (P_r^T beta)); reference src/hmm.cpp:123-127
             const int e = T - 1;
             double wv[NI];
-            double2 pwv[NT];
-            {
-                const double2 *pw = reinterpret_cast<const double2 *>(m.pwtab + ((size_t)e * m.n_span + (adv ? sid : 0)) * MP) + q;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + 4 * nt);
-            }
             if (e == hot) gemv_hot<NS, FRAG>(rF_PT, sF_PT, m.F_PT + (size_t)e * MM, beta, wv, lane);
             else gemv8<NS, false>(m.F_PT + (size_t)e * MM, beta, wv, lane);
             if (storing) store_vec(bv, wv, 1.0);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { wv[2 * nt] *= pwv[nt].x; wv[2 * nt + 1] *= pwv[nt].y; }
+            for (int nt = 0; nt < NT; ++nt) { wv[2 * nt] *= opv[nt].x; wv[2 * nt + 1] *= opv[nt].y; }
             if (e == hot) gemv_hot<NS, FRAG>(rF_PinvT, sF_PinvT, m.F_PinvT + (size_t)e * MM, wv, nb, lane);
             else gemv8<NS, false>(m.F_PinvT + (size_t)e * MM, wv, nb, lane);
         } else {
             // beta <- Td (e_k o beta); reference src/hmm.cpp:139
             if (storing) store_vec(bv, beta, 1.0);
-            const double2 *eq = reinterpret_cast<const double2 *>(m.Eq + (size_t)k * MP + q * NI);
             double tv[NI];
 #pragma unroll
             for (int h = 0; h < NI / 2; ++h) {
-                const double2 ev = __ldg(eq + h);
-                tv[2 * h] = ev.x * beta[2 * h];
-                tv[2 * h + 1] = ev.y * beta[2 * h + 1];
+                tv[2 * h] = opv[h].x * beta[2 * h];
+                tv[2 * h + 1] = opv[h].y * beta[2 * h + 1];
             }
             if constexpr (FRAG == kFragGlobal) gemv8<NS, false>(m.F_Td, tv, nb, lane);
             else gemv8<NS, true>(sF_Td, tv, nb, lane);
@@ -554,6 +618,8 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
         } else {
             --since;
         }
+        fetch_cur();
+        if (adv && active) load_op();
     }
     if (c < p.n_chunks) {
         double part = 0.0;
@@ -567,10 +633,23 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
 }
 
 // ---- launch -------------------------------------------------------------------------------------------------
-static size_t fwd_smem(int NS, int frag)
+// number of span-1 keys whose float step matrix the forward kernel keeps in shared memory (M <= 32 only; option
+// "fwd_cached_keys"): 4 KB each
+static int g_cached_keys = 4;
+void set_fwd_cached_keys(int n) { g_cached_keys = n < 0 ? 0 : (n > 4 ? 4 : n); }
+static int cached_keys(const Model &m)
+{
+    if (m.Mp != 32) return 0;
+    int n = 0;
+    while (n < g_cached_keys && n < 4 && m.hot_keys[n] >= 0) ++n;
+    return n;
+}
+static size_t fwd_smem(int NS, int frag, int nkc = -1)
 {
     const size_t MP = 32 * NS;
-    return (frag == kFragShared ? 2 * MP * MP * sizeof(double) : 0) + (size_t)kMW * 8 * (MP + 4) * sizeof(float);
+    if (nkc < 0) nkc = NS == 1 ? g_cached_keys : 0;
+    return (frag == kFragShared ? 2 * MP * MP * sizeof(double) : 0) + (size_t)kMW * 8 * (MP + 4) * sizeof(float) +
+           (size_t)nkc * MP * MP * sizeof(float);
 }
 static size_t bwd_smem(int NS, int frag)
 {
@@ -597,8 +676,11 @@ int resident_warps_mma(int n_sm, int Mp)
 }
 
 // chunks per warp: 8 when there are enough chunks to give every SM `want` warps, fewer otherwise
+static int g_force_G = 0;   // tests: option "chunks_per_warp" pins G (small inputs otherwise always run with G = 1)
+void set_chunks_per_warp(int g) { g_force_G = (g == 1 || g == 2 || g == 4 || g == 8) ? g : 0; }
 static int chunks_per_warp(int n_chunks, int n_sm)
 {
+    if (g_force_G) return g_force_G;
     const int want = n_sm * 2;
     int G = 8;
     while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
@@ -627,8 +709,8 @@ static void configure_once()
     static bool done = false;
     if (done) return;
     done = true;
-    set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg));
-    set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared));
+    set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg, 4));
+    set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared, 4));
     set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));
     set_attrs(k_backward_mma<1, kFragShared>, bwd_smem(1, kFragShared));
     set_attrs(k_forward_mma<2, kFragShared>, fwd_smem(2, kFragShared));
@@ -643,12 +725,13 @@ void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, 
     const int G = chunks_per_warp(p.n_chunks, n_sm);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
     if (m.Mp == 32) {
-        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg), st>>>(m, p, w, G);
-        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared), st>>>(m, p, w, G);
+        const int nkc = cached_keys(m);
+        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, G, nkc);
+        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared, nkc), st>>>(m, p, w, G, nkc);
     } else if (m.Mp == 64) {
-        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared), st>>>(m, p, w, G);
+        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared), st>>>(m, p, w, G, 0);
     } else {
-        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
+        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal), st>>>(m, p, w, G, 0);
     }
 }
 

@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
     double *bnd = gs + (size_t)K * 32;                                      // [kS32Warps][2][32] boundary key sums
     double *dred = bnd + (size_t)kS32Warps * 2 * 32;                        // [kS32Warps][32]
     int *bkey = reinterpret_cast<int *>(dred + (size_t)kS32Warps * 32);     // [kS32Warps][2]
-    double *pinv_s = reinterpret_cast<double *>(bkey + kS32Warps * 2);      // [4 mt][8 kt][32 lanes] A fragments of Pinv_r
 
     const int Lc = p.chunk_blocks;
     const int64_t colbase = p.col_off[t];
@@ -226,130 +225,165 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
         __syncthreads();
     }
 
-    // ================= span>1 blocks, one pass per eigen key present in the slab =================
-    for (int e = 0; e < NE; ++e) {
-        if (!(mask & (2u << e))) continue;
-        const int l0 = seg[1 + e], l1 = seg[2 + e];
-        const int ngrp = (l1 - l0 + 7) >> 3;
-        const int gbeg = (int)((long)ngrp * warp / kS32Warps), gend = (int)((long)ngrp * (warp + 1) / kS32Warps);
-        // Pinv_r as A fragments in shared memory (permuted index order, see the header): A[a = 4r + mt][i = 8q + kt]
-        {
-            const double *Pinv = m.Pinv + (size_t)e * 1024;
-            for (int x = tid; x < 1024; x += kS32Warps * 32) {
-                const int ln = x & 31, kt = (x >> 5) & 7, mt = x >> 8;
-                pinv_s[x] = Pinv[(4 * (ln >> 2) + mt) * 32 + 8 * (ln & 3) + kt];   // A[a = 4r + mt][i = 8q + kt]
-            }
-            __syncthreads();
-        }
-        double invd[4];
+}
+
+// ================= span>1 blocks: R_e and D_e, one CTA per work item (Plan::erec) =================
+// An item holds span>1 blocks of ONE (contig, eigen key) in span-id order.  Per block l (eigen coordinates a, b):
+//     u = Pinv_r alpha_hat_{l-1}  (stored by the forward pass),   w = P_r^T beta_l  (stored by the backward pass),
+//     pw = d~^span,   C = 1 / (scale sum_a pw_a u_a w_a),   y = C w
+//     R_e(a, b) += u_a y_b (pw_a - pw_b),      D_e(a) += span d~_a^(span-1) u_a y_a
+// Blocks of equal span share pw, so a run of them accumulates G += u y^T (ONE rank-1 DMMA stream, k = blocks) and is
+// weighted once when the run ends: R_e += G o (pw_a - pw_b).  Groups of 4 blocks that straddle a run boundary (or
+// data whose spans are all different) take the direct rank-2 form G += (u o pw) y^T - u (y o pw)^T and are added
+// unweighted.  Each warp keeps its R_e accumulator in shared memory (touched once per run) and G in registers.
+constexpr int kSEWarps = 4;
+
+__global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, Work w)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tiles = reinterpret_cast<double *>(smem_raw);                 // [kSEWarps][32*33]
+    double *dred = tiles + (size_t)kSEWarps * 32 * 33;                    // [kSEWarps][32]
+    const int item = blockIdx.x;
+    const int t = p.it_contig[item], e = p.it_eig[item], n = p.it_len[item];
+    const int64_t g0 = p.blk_off[t];
+    const int2 *rec = p.erec + p.it_start[item];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    double *tile = tiles + (size_t)warp * 32 * 33;
+    for (int x = lane; x < 32 * 33; x += 32) tile[x] = 0.0;
+    __syncwarp();
+
+    const int ngrp = (n + 3) >> 2;
+    const int gbeg = (int)((long)ngrp * warp / kSEWarps), gend = (int)((long)ngrp * (warp + 1) / kSEWarps);
+    const double sc = m.scale[e];
+    double invd[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const double dv = m.dsc[e * 32 + 4 * r + mt];
+        invd[mt] = dv != 0.0 ? 1.0 / dv : 0.0;
+    }
+    const double *pwbase = m.pwtab + (size_t)e * m.n_span * 32 + 4 * r;
+
+    double G[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) G[i][j][0] = G[i][j][1] = 0.0;
+    double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+    double pwrow[4] = {0.0, 0.0, 0.0, 0.0};   // pw[4r .. 4r+3] of the current uniform run
+    int mode = 0, run_sid = -1;               // 0: G empty, 1: uniform run of span id run_sid, 2: rank-2 (already weighted)
+
+    // G -> this warp's R_e tile; tile (mt, nt) of the C fragment: row a = 4r + mt, columns b = 4 (2q + h) + nt
+    auto fold = [&]() {
+        if (mode == 0) return;
+        double pc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) pc[h][nt] = __shfl_sync(kFullMask, pwrow[nt], 4 * (2 * q + h));   // pw[4 (2q + h) + nt]
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double wgt = mode == 1 ? pwrow[mt] - pc[h][nt] : 1.0;
+                    double *dst = tile + (4 * r + mt) * 33 + 4 * (2 * q + h) + nt;
+                    *dst = fma(G[mt][nt][h], wgt, *dst);
+                    G[mt][nt][h] = 0.0;
+                }
+        mode = 0;
+    };
+
+    // software pipeline: records two groups ahead, operands one group ahead (lane (r, q): block q of the group, rows 4r..4r+3)
+    struct Ops { dbl4 u, w, pw; int span, sid; bool valid; };
+    auto load_rec = [&](int g) { return (g < gend && 4 * g + q < n) ? __ldg(rec + 4 * g + q) : make_int2(-1, 0); };
+    auto load_ops = [&](int2 rc) {
+        Ops o;
+        o.valid = rc.x >= 0;
+        o.sid = rc.y;
+        const int64_t gb = g0 + (o.valid ? rc.x : 0);
+        o.u = ld4d(w.uvec + (size_t)gb * 32 + 4 * r);
+        o.w = ld4d(w.bvec + (size_t)gb * 32 + 4 * r);
+        o.pw = ld4d(pwbase + (size_t)rc.y * 32);
+        o.span = __ldg(m.span_list + rc.y);
+        return o;
+    };
+    int2 rc1 = load_rec(gbeg + 1);
+    Ops nxt = load_ops(load_rec(gbeg));
+    for (int g = gbeg; g < gend; ++g) {
+        const Ops cur = nxt;
+        nxt = load_ops(rc1);
+        rc1 = load_rec(g + 2);
+
+        double uv[4], yv[4], pw[4], dot = 0.0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-            const double dv = m.dsc[e * 32 + 4 * r + mt];
-            invd[mt] = dv != 0.0 ? 1.0 / dv : 0.0;
+            uv[mt] = cur.valid ? cur.u.v[mt] : 0.0;
+            pw[mt] = cur.pw.v[mt];
+            dot = fma(pw[mt] * uv[mt], cur.w.v[mt], dot);
         }
-        const double sc = m.scale[e];
-        double acc[4][4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        double dacc[4] = {0.0, 0.0, 0.0, 0.0};
-        int2 rBn = (gbeg < gend && l0 + 8 * gbeg + r < l1) ? __ldg(rec + l0 + 8 * gbeg + r) : make_int2(-1, 0);
-        int2 rHn0 = (gbeg < gend && l0 + 8 * gbeg + 2 * q < l1) ? __ldg(rec + l0 + 8 * gbeg + 2 * q) : make_int2(-1, 0);
-        int2 rHn1 = (gbeg < gend && l0 + 8 * gbeg + 2 * q + 1 < l1) ? __ldg(rec + l0 + 8 * gbeg + 2 * q + 1) : make_int2(-1, 0);
-        for (int g = gbeg; g < gend; ++g) {
-            const int base = l0 + 8 * g;
-            const int2 rB = rBn, rH0 = rHn0, rH1 = rHn1;
-            {
-                const int nb = base + 8;
-                const bool more = g + 1 < gend;
-                rBn = (more && nb + r < l1) ? __ldg(rec + nb + r) : make_int2(-1, 0);
-                rHn0 = (more && nb + 2 * q < l1) ? __ldg(rec + nb + 2 * q) : make_int2(-1, 0);
-                rHn1 = (more && nb + 2 * q + 1 < l1) ? __ldg(rec + nb + 2 * q + 1) : make_int2(-1, 0);
-            }
-            // U = Pinv_r [alpha_prev of 8 blocks]: B[i = 4kt + q][block r]
-            double u[4][2];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) u[mt][0] = u[mt][1] = 0.0;
-            {
-                const bool vr = rB.x >= 0;
-                const int br = vr ? rB.x : 0;
-                const flt8 a8 = ld8f(alpha_col(br) + 8 * q);   // states 8q .. 8q+7 of block r
-#pragma unroll
-                for (int kt = 0; kt < 8; ++kt) {
-                    const double bfr = vr ? (double)a8.v[kt] : 0.0;
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) dmma884(u[mt][0], u[mt][1], pinv_s[(mt * 8 + kt) * 32 + lane], bfr);
-                }
-            }
-            // per lane: blocks 2q + h, states 8mt + r
-            double xs[4][2], ys[4][2], zs[4][2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int2 rc = h == 0 ? rH0 : rH1;
-                const bool vb = rc.x >= 0;
-                const int64_t gb = g0 + (vb ? rc.x : 0);
-                const int span = vb ? __ldg(m.span_list + rc.y) : 2;
-                const double *bv = w.bvec + (size_t)gb * 32;
-                const double *pwr = m.pwtab + ((size_t)e * m.n_span + (vb ? rc.y : 0)) * 32;
-                double wv[4], pw[4], dot = 0.0;
-                const dbl4 w4 = ld4d(bv + 4 * r), p4 = ld4d(pwr + 4 * r);   // eigen indices 4r .. 4r+3
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    wv[mt] = vb ? w4.v[mt] : 0.0;
-                    pw[mt] = p4.v[mt];
-                    dot = fma(pw[mt] * u[mt][h], wv[mt], dot);
-                }
-                dot = sum_over_r(dot);
-                const double C = vb ? 1.0 / (sc * dot) : 0.0;
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    const double y = C * wv[mt];
-                    xs[mt][h] = u[mt][h] * pw[mt];
-                    ys[mt][h] = y;
-                    zs[mt][h] = y * pw[mt];
-                    dacc[mt] = fma(y * u[mt][h] * (double)span, pw[mt] * invd[mt], dacc[mt]);
-                }
-            }
-            // R += X Y^T - U Z^T over the 8 blocks (two k-tiles: blocks {2q} and {2q+1})
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        dmma884(acc[mt][nt][0], acc[mt][nt][1], xs[mt][h], ys[nt][h]);
-                        dmma884(acc[mt][nt][0], acc[mt][nt][1], -u[mt][h], zs[nt][h]);
-                    }
-        }
-        store_acc(tiles + (size_t)warp * 32 * 33, acc, r, q);
+        dot = sum_over_r(dot);
+        const double C = cur.valid ? 1.0 / (sc * dot) : 0.0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-            const double v = sum_over_q(dacc[mt]);
-            if (q == 0) dred[warp * 32 + 4 * r + mt] = v;
+            yv[mt] = cur.valid ? C * cur.w.v[mt] : 0.0;
+            dacc[mt] = fma(yv[mt] * uv[mt] * (double)cur.span, pw[mt] * invd[mt], dacc[mt]);
         }
-        __syncthreads();
-        double *Rp = w.Rpart + ((size_t)slab * NE + e) * 1024;
-        for (int x = tid; x < 1024; x += kS32Warps * 32) {
-            const int i = x >> 5, j = x & 31;
-            double s = 0.0;
+        const int s0 = __shfl_sync(kFullMask, cur.sid, 0);       // entry 0 of a group is always valid
+        const bool uni = __all_sync(kFullMask, !cur.valid || cur.sid == s0);
+        if (uni) {
+            if (mode != 1 || run_sid != s0) {
+                fold();
+                mode = 1;
+                run_sid = s0;
 #pragma unroll
-            for (int ww = 0; ww < kS32Warps; ++ww) s += tiles[(size_t)ww * 32 * 33 + i * 33 + j];
-            Rp[x] = s;
-        }
-        if (tid < 32) {
-            double s = 0.0;
+                for (int i = 0; i < 4; ++i) pwrow[i] = __shfl_sync(kFullMask, pw[i], lane & ~3);   // block 0's row
+            }
 #pragma unroll
-            for (int ww = 0; ww < kS32Warps; ++ww) s += dred[ww * 32 + tid];
-            w.dpart[((size_t)slab * NE + e) * 32 + tid] = s;
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(G[mt][nt][0], G[mt][nt][1], uv[mt], yv[nt]);
+        } else {
+            if (mode != 2) { fold(); mode = 2; }
+            double xv[4], zv[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) { xv[mt] = uv[mt] * pw[mt]; zv[mt] = yv[mt] * pw[mt]; }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    dmma884(G[mt][nt][0], G[mt][nt][1], xv[mt], yv[nt]);
+                    dmma884(G[mt][nt][0], G[mt][nt][1], -uv[mt], zv[nt]);
+                }
         }
-        __syncthreads();
+    }
+    fold();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const double v = sum_over_q(dacc[mt]);
+        if (q == 0) dred[warp * 32 + 4 * r + mt] = v;
+    }
+    __syncthreads();
+    double *Rp = w.Ritem + (size_t)item * 1024;
+    for (int x = tid; x < 1024; x += kSEWarps * 32) {
+        const int i = x >> 5, j = x & 31;
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kSEWarps; ++ww) s += tiles[(size_t)ww * 32 * 33 + i * 33 + j];
+        Rp[x] = s;
+    }
+    if (tid < 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kSEWarps; ++ww) s += dred[ww * 32 + tid];
+        w.ditem[(size_t)item * 32 + tid] = s;
     }
 }
 
 size_t stats32_smem_bytes(const Model &m)
 {
-    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32 + 1024) * sizeof(double) +
+    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32) * sizeof(double) +
            (size_t)kS32Warps * 2 * sizeof(int);
 }
 
@@ -362,6 +396,15 @@ void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t s
         configured = smem;
     }
     k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w);
+    if (p.n_items > 0) {
+        const size_t smem_e = ((size_t)kSEWarps * 32 * 33 + (size_t)kSEWarps * 32) * sizeof(double);
+        static bool configured_e = false;
+        if (!configured_e) {
+            cudaFuncSetAttribute(k_stats32e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+            configured_e = true;
+        }
+        k_stats32e<<<p.n_items, kSEWarps * 32, smem_e, st>>>(m, p, w);
+    }
 }
 
 }  // namespace smcb

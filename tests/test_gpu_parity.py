@@ -71,6 +71,61 @@ def test_golden_chunked_tensor_path(name, chunk, burn):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("G", [8, 2])
+def test_golden_tensor_path_several_chunks_per_warp(name, G):
+    """Small inputs run with one chunk per warp; pin 8 (and 2) so that every row of the MMA carries a chunk."""
+    g = Golden(name)
+    ctx = capi.Context(0)
+    try:
+        ctx.set_option("chunks_per_warp", G)
+        for k, v in {"chunk_blocks": 48, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": 1}.items():
+            ctx.set_option(k, v)
+        ctx.set_contigs(g.contigs, g.npop)
+        out = ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+        check_against(out, g.ref)
+    finally:
+        ctx.set_option("chunks_per_warp", 0)
+        ctx.close()
+
+
+@pytest.mark.parametrize("name,G,cached", [("c2_1500", 1, 4), ("c2_1500", 8, 4), ("c2_1500", 8, 0), ("c1_2k", 8, 2), ("m64_600", 8, 4),
+                                           ("m17_800", 4, 4), ("c4_twopop_1200", 8, 1)])
+def test_tensor_path_float_step_is_bit_exact(name, G, cached):
+    """A contig of span-1 blocks only exercises nothing but the float GEMV step of the tensor-path forward kernel (packed
+    FFMA2 arithmetic, step matrices in shared or global memory): every alpha_hat column must equal the reference
+    semantics (the port, pinned bit for bit to the reference in tests/test_oracle.py) exactly."""
+    g = Golden(name)
+    contigs = []
+    for c in g.contigs:
+        c = c.copy()
+        c[:, 0] = 1
+        contigs.append(c)
+    ref = dict(g.ref)
+    for k in ("eig_P", "eig_Pinv", "eig_d", "eig_dscaled", "eig_scale", "eig_key_idx"):
+        ref[k] = g.ref[k][:0]
+    ctx = capi.Context(0)
+    try:
+        ctx.set_option("chunks_per_warp", G)
+        ctx.set_option("fwd_cached_keys", cached)
+        for k, v in {"chunk_blocks": 150, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": 1}.items():
+            ctx.set_option(k, v)
+        ctx.set_contigs(contigs, g.npop, g.ref["keys"])
+        assert len(ctx.eig_keys) == 0
+        out = ctx.estep(ref["pi"], ref["T"], ref["E"], ref)
+        for c, obs in enumerate(contigs):
+            o = port.hmm_estep(obs, ref, want_alpha=True)
+            a = ctx.debug_alpha_hat(c)
+            assert np.array_equal(a[:151], o["alpha_hat"][:151]), "chunk 0 follows the reference chain from pi: must be exact"
+            assert (a == o["alpha_hat"]).mean() > 0.999      # later chunks start from a burn-in state (float-converged)
+            assert abs(out["ll"][c] - o["ll"]) <= 1e-11 * abs(o["ll"])
+            assert relmax(out["xisum"][c], o["xisum"]) <= STAT_RTOL
+    finally:
+        ctx.set_option("chunks_per_warp", 0)
+        ctx.set_option("fwd_cached_keys", 4)
+        ctx.close()
+
+
 @pytest.mark.parametrize("name", ["c1_2k", "c2_1500", "m17_800", "m64_600", "ref_test_inference"])
 def test_golden_library_eigensystems(name):
     g = Golden(name)
