@@ -16,7 +16,7 @@
 
 namespace smcb {
 
-constexpr int kS32Warps = 8;
+constexpr int kS32Warps = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -132,38 +132,41 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                 first_open = false;
             }
         };
-        // the (block index, key) record of the next group is fetched one iteration ahead: no dependent load chain
-        int2 rnext = (gbeg < gend && d0 + 4 * gbeg + q < d1) ? __ldg(rec + d0 + 4 * gbeg + q) : make_int2(0, -1);
-        for (int g = gbeg; g < gend; ++g) {
-            const int2 rc = rnext;
-            rnext = (g + 1 < gend && d0 + 4 * (g + 1) + q < d1) ? __ldg(rec + d0 + 4 * (g + 1) + q) : make_int2(0, -1);
-            const bool valid = rc.y >= 0;
-            const int b = rc.x;
-            const int64_t gb = g0 + b;
-            const int k = rc.y;
-            double av[4], bvv[4], vv[4], be[4], ac[4], ek[4];
-            double pp = 0.0, cn = 1.0;
-            if (valid) {
-                const float *ap = alpha_col(b);
-                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ap) + r), c4 = __ldg(reinterpret_cast<const float4 *>(ap + 32) + r);
-                const dbl4 b4 = ld4d(w.bvec + (size_t)gb * 32 + 4 * r), e4 = ld4d(m.E + (size_t)k * 32 + 4 * r);
-                av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
-                ac[0] = c4.x; ac[1] = c4.y; ac[2] = c4.z; ac[3] = c4.w;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { be[i] = b4.v[i]; ek[i] = e4.v[i]; }
-                cn = (double)w.cnorm[gb];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { av[i] = 0.0; ac[i] = 0.0; be[i] = 0.0; ek[i] = 0.0; }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pp = fma(ac[i], be[i], pp);
-            pp = sum_over_r(pp);                                      // p = alpha_l . beta_l   (all lanes take part)
-            const double inv_p = valid ? 1.0 / pp : 0.0;
-            const double inv_cp = inv_p / cn;                         // 1 / (c_l p_l)
+        // Software pipeline, two groups (8 blocks) per iteration: the records run two iterations ahead of the arithmetic and
+        // the operands one, so ~4 KB per warp are in flight while the previous groups are on the tensor pipe.
+        struct Ops { float4 a4, c4; dbl4 b4, e4; float cn; int k; };      // k < 0: padding entry
+        auto load_rec = [&](int g) { return (g < gend && d0 + 4 * g + q < d1) ? __ldg(rec + d0 + 4 * g + q) : make_int2(0, -1); };
+        auto load_ops = [&](int2 rc) {
+            Ops o;
+            o.k = rc.y;
+            const int64_t gb = g0 + rc.x;
+            const float *ap = alpha_col(rc.x);
+            o.a4 = __ldg(reinterpret_cast<const float4 *>(ap) + r);
+            o.c4 = __ldg(reinterpret_cast<const float4 *>(ap + 32) + r);
+            o.b4 = ld4d(w.bvec + (size_t)gb * 32 + 4 * r);
+            o.e4 = ld4d(m.E + (size_t)(rc.y < 0 ? 0 : rc.y) * 32 + 4 * r);
+            o.cn = __ldg(w.cnorm + gb);
+            return o;
+        };
+        auto process = [&](const Ops &o) {
+            const bool valid = o.k >= 0;
+            const int k = o.k;
+            double av[4], ac[4], be[4], bvv[4], vv[4];
+            av[0] = o.a4.x; av[1] = o.a4.y; av[2] = o.a4.z; av[3] = o.a4.w;
+            ac[0] = o.c4.x; ac[1] = o.c4.y; ac[2] = o.c4.z; ac[3] = o.c4.w;
+            double pp = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                bvv[i] = be[i] * ek[i] * inv_cp;
+                if (!valid) { av[i] = 0.0; ac[i] = 0.0; }
+                be[i] = valid ? o.b4.v[i] : 0.0;
+                pp = fma(ac[i], be[i], pp);
+            }
+            pp = sum_over_r(pp);                                      // p = alpha_l . beta_l   (all lanes take part)
+            const double inv_p = valid ? 1.0 / pp : 0.0;
+            const double inv_cp = valid ? inv_p / (double)o.cn : 0.0; // 1 / (c_l p_l)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bvv[i] = be[i] * o.e4.v[i] * inv_cp;
                 vv[i] = ac[i] * be[i] * inv_p;
             }
 #pragma unroll
@@ -188,6 +191,17 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                     }
                 }
             }
+        };
+        int2 rcA = load_rec(gbeg + 2), rcB = load_rec(gbeg + 3);
+        Ops nA = load_ops(load_rec(gbeg)), nB = load_ops(load_rec(gbeg + 1));
+        for (int g = gbeg; g < gend; g += 2) {
+            const Ops cA = nA, cB = nB;
+            nA = load_ops(rcA);
+            nB = load_ops(rcB);
+            rcA = load_rec(g + 4);
+            rcB = load_rec(g + 5);
+            process(cA);
+            if (g + 1 < gend) process(cB);
         }
         // the last key of the range may be shared with the next warp: boundary slot 1 (slot 0 if it is also the first)
         if (cur >= 0) {
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
 // unweighted.  Each warp keeps its R_e accumulator in shared memory (touched once per run) and G in registers.
 constexpr int kSEWarps = 4;
 
-__global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, Work w)
+__global__ void __launch_bounds__(kSEWarps * 32, 2) k_stats32e(Model m, Plan p, Work w)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);                 // [kSEWarps][32*33]
@@ -256,12 +270,6 @@ __global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, 
     const int ngrp = (n + 3) >> 2;
     const int gbeg = (int)((long)ngrp * warp / kSEWarps), gend = (int)((long)ngrp * (warp + 1) / kSEWarps);
     const double sc = m.scale[e];
-    double invd[4];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const double dv = m.dsc[e * 32 + 4 * r + mt];
-        invd[mt] = dv != 0.0 ? 1.0 / dv : 0.0;
-    }
     const double *pwbase = m.pwtab + (size_t)e * m.n_span * 32 + 4 * r;
 
     double G[4][4][2];
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, 
     };
 
     // software pipeline: records two groups ahead, operands one group ahead (lane (r, q): block q of the group, rows 4r..4r+3)
-    struct Ops { dbl4 u, w, pw; int span, sid; bool valid; };
+    struct Ops { dbl4 u, w, pw; double span; int sid; bool valid; };
     auto load_rec = [&](int g) { return (g < gend && 4 * g + q < n) ? __ldg(rec + 4 * g + q) : make_int2(-1, 0); };
     auto load_ops = [&](int2 rc) {
         Ops o;
@@ -306,16 +314,10 @@ __global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, 
         o.u = ld4d(w.uvec + (size_t)gb * 32 + 4 * r);
         o.w = ld4d(w.bvec + (size_t)gb * 32 + 4 * r);
         o.pw = ld4d(pwbase + (size_t)rc.y * 32);
-        o.span = __ldg(m.span_list + rc.y);
+        o.span = (double)__ldg(m.span_list + rc.y);
         return o;
     };
-    int2 rc1 = load_rec(gbeg + 1);
-    Ops nxt = load_ops(load_rec(gbeg));
-    for (int g = gbeg; g < gend; ++g) {
-        const Ops cur = nxt;
-        nxt = load_ops(rc1);
-        rc1 = load_rec(g + 2);
-
+    auto process = [&](const Ops &cur) {
         double uv[4], yv[4], pw[4], dot = 0.0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, 
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             yv[mt] = cur.valid ? C * cur.w.v[mt] : 0.0;
-            dacc[mt] = fma(yv[mt] * uv[mt] * (double)cur.span, pw[mt] * invd[mt], dacc[mt]);
+            dacc[mt] = fma(yv[mt] * uv[mt], cur.span * pw[mt], dacc[mt]);   // 1 / d~_a is applied once, after the loop
         }
         const int s0 = __shfl_sync(kFullMask, cur.sid, 0);       // entry 0 of a group is always valid
         const bool uni = __all_sync(kFullMask, !cur.valid || cur.sid == s0);
@@ -357,11 +359,23 @@ __global__ void __launch_bounds__(kSEWarps * 32, 3) k_stats32e(Model m, Plan p, 
                     dmma884(G[mt][nt][0], G[mt][nt][1], -uv[mt], zv[nt]);
                 }
         }
+    };
+    int2 rcA = load_rec(gbeg + 2), rcB = load_rec(gbeg + 3);
+    Ops nA = load_ops(load_rec(gbeg)), nB = load_ops(load_rec(gbeg + 1));
+    for (int g = gbeg; g < gend; g += 2) {
+        const Ops cA = nA, cB = nB;
+        nA = load_ops(rcA);
+        nB = load_ops(rcB);
+        rcA = load_rec(g + 4);
+        rcB = load_rec(g + 5);
+        process(cA);
+        if (g + 1 < gend) process(cB);
     }
     fold();
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-        const double v = sum_over_q(dacc[mt]);
+        const double dv = m.dsc[e * 32 + 4 * r + mt];
+        const double v = sum_over_q(dacc[mt]) * (dv != 0.0 ? 1.0 / dv : 0.0);
         if (q == 0) dred[warp * 32 + 4 * r + mt] = v;
     }
     __syncthreads();
