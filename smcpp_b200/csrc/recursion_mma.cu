@@ -239,6 +239,19 @@ void launch_setup_frags(const Model &m, cudaStream_t st)
     k_setup_frags<<<blocks, 256, 0, st>>>(m);
 }
 
+// Predicated loads that write their destination IN PLACE (it keeps its value when the predicate is false).  A plain
+// `if (p) x = load` on a loop-carried register compiles to a load into a scratch register plus a move, and the move
+// waits for the load right where it was issued (ncu r1h: 4-5 % of each recursion kernel at the batch rotation).
+__device__ __forceinline__ void ldg_if(int &dst, const int32_t *ptr, bool pred)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.b32 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
+}
+__device__ __forceinline__ void ldg_if(int &dst, const uint16_t *ptr, bool pred)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.u16 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
+}
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 // ---- shared per-chunk bookkeeping -------------------------------------------------------------------------
 struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of the lane's chunk: lane q holds blocks q and 4 + q
     int sp_lo, sp_hi, kc_lo, kc_hi, id_lo, id_hi;
@@ -413,11 +426,27 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             float y[NI];
 #pragma unroll
             for (int idx = 0; idx < NI / 2; ++idx) unpack2(y2[idx], y[2 * idx], y[2 * idx + 1]);
-            __syncwarp();
+            if (M == MP) {
+                // Eigen's sum() order for 32 NS aligned floats (eigen_sum_f32_full: packets p0 / p1 accumulate the
+                // coefficients = c and = 4 + c (mod 8), then p0 + p1, then (x + z) + (y + w)) without a trip through shared
+                // memory: lane q holds exactly the coefficients = 2q, 2q + 1 (mod 8), in ascending order, so its two
+                // chains are p0.x/p0.y (q = 0), p0.z/p0.w (q = 1), p1.x/p1.y (q = 2), p1.z/p1.w (q = 3); the rest is
+                // two butterfly steps (float addition commutes exactly).
+                float ev = y[0], od = y[1];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
-            __syncwarp();
-            sf = M == MP ? eigen_sum_f32_full<MP>(xs) : eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
+                for (int gq = 1; gq < NI / 2; ++gq) { ev = __fadd_rn(ev, y[2 * gq]); od = __fadd_rn(od, y[2 * gq + 1]); }
+                ev = __fadd_rn(ev, __shfl_xor_sync(kAll, ev, 2));     // q in {0, 2}: t.x, others: t.z
+                od = __fadd_rn(od, __shfl_xor_sync(kAll, od, 2));     //              t.y          t.w
+                ev = __fadd_rn(ev, __shfl_xor_sync(kAll, ev, 1));     // t.x + t.z
+                od = __fadd_rn(od, __shfl_xor_sync(kAll, od, 1));     // t.y + t.w
+                sf = __fadd_rn(ev, od);
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2 *>(xs + 8 * nt + 2 * q) = make_float2(y[2 * nt], y[2 * nt + 1]);
+                __syncwarp();
+                sf = eigen_sum_f32(xs, M, (M & 3) ? (int)((4 - (((long)(cur + 1) * M) & 3)) & 3) : 0);
+            }
 #pragma unroll
             for (int idx = 0; idx < NI; ++idx) xn[idx] = __fdiv_rn(y[idx], sf);
             cmul = (double)sf;
@@ -442,10 +471,28 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             ++cur;
             ++done;
             if (cur >= bend) active = false;
-            else if (cur - base == 8) { base += 8; ob = obn; obn = load_batch(base + 8); }
+        }
+        {
+            const bool rot = adv && active && cur - base == 8;
+            if (rot) { base += 8; ob = obn; }
+            const int64_t i0 = g0 + min(base + 8 + q, bend - 1), i1 = g0 + min(base + 12 + q, bend - 1);
+            ldg_if(obn.sp_lo, p.span + i0, rot); ldg_if(obn.kc_lo, p.kcode + i0, rot); ldg_if(obn.id_lo, p.span_id + i0, rot);
+            ldg_if(obn.sp_hi, p.span + i1, rot); ldg_if(obn.kc_hi, p.kcode + i1, rot); ldg_if(obn.id_hi, p.span_id + i1, rot);
         }
         fetch_cur();
         if (adv && active && (kc >> 11) > 0) load_pw();
+        if constexpr (NS == 1) {
+            // float step matrix of the block AFTER the next one -> L1 (one full round ahead).  The matrices of the rare keys
+            // (60+ full-SFS keys, 4 KB each) do not stay in L1; without this every 4-row group of their GEMV waits on L2.
+            const int pos2 = cur + 1 - base;
+            const int v2 = pos2 < 8 ? ((pos2 & 4) ? ob.kc_hi : ob.kc_lo) : obn.kc_lo;
+            const int kc2 = __shfl_sync(kAll, v2, (lane & ~3) | (pos2 & 3));
+            if (adv && active && cur + 1 < bend && (kc2 >> 11) == 0 && (kc2 & 2047) != m.hot_keys[0]) {
+                const float *row = m.A32q + ((size_t)(kc2 & 2047) * MP + 8 * q) * 4 * NI;   // rows 8q .. 8q + 7, 128 B each
+#pragma unroll
+                for (int j = 0; j < 8; ++j) prefetch_l1(row + (size_t)j * 4 * NI);
+            }
+        }
     }
     if (c < p.n_chunks) {
         store_col(w.end_alpha + (size_t)c * MP);
@@ -614,9 +661,15 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
             --cur;
             ++done;
             if (cur < s) active = false;
-            else if (top - cur == 8) { top -= 8; ob = obn; obn = load_batch(top - 8); }
         } else {
             --since;
+        }
+        {
+            const bool rot = adv && active && top - cur == 8;
+            if (rot) { top -= 8; ob = obn; }
+            const int64_t i0 = g0 + max(top - 8 - q, s), i1 = g0 + max(top - 12 - q, s);
+            ldg_if(obn.kc_lo, p.kcode + i0, rot); ldg_if(obn.id_lo, p.span_id + i0, rot);
+            ldg_if(obn.kc_hi, p.kcode + i1, rot); ldg_if(obn.id_hi, p.span_id + i1, rot);
         }
         fetch_cur();
         if (adv && active) load_op();
