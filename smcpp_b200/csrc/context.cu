@@ -487,19 +487,42 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         // double the time), but never shorter than the burn-in, which bounds the redundant work by 2x
         int target = ctx->opt_target_warps;
         const bool tensor_path = Mp == 32 || Mp == 64 || Mp == 128;
-        if (target <= 0) target = tensor_path ? std::min(resident_warps_mma(ctx->n_sm, Mp), ctx->n_sm * 8) * 8 : ctx->n_sm * 16;
         auto chunks_for = [&](int64_t lc) {
             int64_t n = 0;
             for (int c = 0; c < ctx->C; ++c) n += (ctx->blk_off[c + 1] - ctx->blk_off[c] + lc - 1) / lc;
             return n;
         };
-        int64_t lo = std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
-        if (chunks_for(lo) <= target) hi = lo;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) / 2;
-            if (chunks_for(mid) <= target) hi = mid; else lo = mid + 1;
+        auto min_lc_for = [&](int64_t tgt) {   // shortest chunk length (>= burn-in) that needs at most tgt chunks
+            int64_t lo = std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
+            if (chunks_for(lo) <= tgt) hi = lo;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) / 2;
+                if (chunks_for(mid) <= tgt) hi = mid; else lo = mid + 1;
+            }
+            return hi;
+        };
+        if (target > 0 || !tensor_path) {
+            if (target <= 0) target = ctx->n_sm * 16;
+            Lc = (int)min_lc_for(target);
+        } else {
+            // Tensor-path recursions: a CTA carries 4 warps x 8 chunks and the forward and backward kernels share the SMs,
+            // so the chunk count is a whole number of CTAs per SM -- a partial layer leaves most SMs half empty while the
+            // full ones set the pace (3 contigs x 10^6 blocks: 5 862 chunks 3.14 ms, 4 734 chunks 2.18 ms).  One or two
+            // CTAs per SM and kernel: measured cost of one chunk step at M = 32 is ~3 750 cycles with one CTA of each
+            // kernel on an SM and ~5 460 with two (profiles/r1h), so the shorter schedule wins below ~4 x 10^6 blocks.
+            const int per_layer = ctx->n_sm * 32;
+            const int layers = std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp), ctx->n_sm * 8) / (ctx->n_sm * 4)));
+            const double step_cost[3] = {0.0, 3750.0, 5460.0};
+            double best = 0.0;
+            Lc = 0;
+            for (int k = 1; k <= layers; ++k) {
+                const int64_t lc = min_lc_for((int64_t)per_layer * k);
+                const int64_t n = chunks_for(lc);
+                const int used = (int)std::min<int64_t>(layers, (n + per_layer - 1) / per_layer);
+                const double cost = (double)(std::min<int64_t>(lc, maxL) + burn) * step_cost[std::max(1, used)];
+                if (Lc == 0 || cost < best) { best = cost; Lc = (int)lc; }
+            }
         }
-        Lc = (int)hi;
     }
     if (Lc > maxL) Lc = (int)maxL;
     if (Lc < 1) Lc = 1;

@@ -122,7 +122,7 @@ def test_tensor_path_float_step_is_bit_exact(name, G, cached):
             assert relmax(out["xisum"][c], o["xisum"]) <= STAT_RTOL
     finally:
         ctx.set_option("chunks_per_warp", 0)
-        ctx.set_option("fwd_cached_keys", 4)
+        ctx.set_option("fwd_cached_keys", 0)
         ctx.close()
 
 
