@@ -317,7 +317,8 @@ def main():
                          # dram__bytes_read+write of k_forward32m + k_backward32m, one launch each (profiles/r1f_summary.md);
                          # measured for this workload on one GPU only
                          "traffic": 8.98e9 if (cfg == "C3" and world == 1) else None, "peak_source": peak_src,
-                         "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms},
+                         "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms,
+                         "kernel_ms_per_step": [round(float(x), 3) for x in ms_rec]},
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
                               "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},

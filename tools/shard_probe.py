@@ -7,7 +7,7 @@ z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 model = {k: z[k] for k in z.files}
 ids = [int(x) for x in sys.argv[1].split(",")]
 contigs = [synth.make_contig(1_000_000, (20,), 1000 + c, 1) for c in ids]
-variants = [{}, {"target_warps": 4736}, {"target_warps": 7104}, {"target_warps": 2368}]
+variants = [{}]
 for opts in variants:
     ctx = capi.Context(0)
     for k, v in opts.items(): ctx.set_option(k, v)
@@ -18,6 +18,6 @@ for opts in variants:
         st = ctx.stats()
         if i and (best is None or st["ms_total"] < best["ms_total"]): best = st
     print(len(ids), opts, "chunks", best["n_chunks"], "Lc", best["chunk_blocks"], "total %.2f fwd||bwd %.2f stats %.2f" % (best["ms_total"], best["ms_forward"], best["ms_stats"]),
-          "sweeps", best["fwd_sweeps"], best["bwd_sweeps"], flush=True)
+          "burn", best["burn_in_blocks"], "mm %.2e %.2e" % (best["fwd_max_mismatch"], best["bwd_max_mismatch"]), "lockstep %.4f" % (best["mma_steps"] / max(1, 8 * best["mma_rounds"])), "fwd-only %.2f bwd-only %.2f" % (best["ms_forward_only"], best["ms_backward"]), flush=True)
     ctx.set_option("chunks_per_warp", 0)
     ctx.close()
