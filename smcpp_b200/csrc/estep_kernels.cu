@@ -220,7 +220,9 @@ void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cuda
     }
 }
 
-__global__ void k_check_forward(Model m, Plan p, Work w, float tol)
+// tol0 applies to a chunk that still carries its burn-in start (two independent float trajectories), tol to a chunk
+// that has been re-run from its neighbour's end value (see smcpp_b200_ctx::opt_fwd_tol)
+__global__ void k_check_forward(Model m, Plan p, Work w, float tol0, float tol)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
@@ -233,16 +235,17 @@ __global__ void k_check_forward(Model m, Plan p, Work w, float tol)
             df = fmaxf(df, fabsf(a[j] - b[j]));
         }
         const float rel = mx > 0.f ? df / mx : df;
-        flag = rel > tol;
+        flag = rel > (w.fwd_rerun[c] ? tol : tol0);
         if (rel > 0.f) atomicMax(&w.counters[2], __float_as_int(rel));
     }
     w.fwd_flag[c] = flag;
+    if (flag) w.fwd_rerun[c] = 1;
     if (flag) atomicAdd(&w.counters[0], 1);
 }
 
-void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st)
+void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st)
 {
-    k_check_forward<<<(p.n_chunks + 127) / 128, 128, 0, st>>>(m, p, w, tol);
+    k_check_forward<<<(p.n_chunks + 127) / 128, 128, 0, st>>>(m, p, w, tol0, tol);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -112,7 +112,8 @@ struct Work {
     double *beta_out;        // [n_chunks][Mp] beta at the chunk's left end
     double *beta_out_prev;   // [n_chunks][Mp]
     uint8_t *fwd_flag;       // [n_chunks] 1 = must be (re)run in the next sweep
-    uint8_t *bwd_flag;       // [n_chunks]
+    uint8_t *bwd_flag;
+    uint8_t *fwd_rerun;      // [n_chunks] 1 = the chunk has been re-run from its neighbour's end value in this E-step       // [n_chunks]
     int *counters;           // [8]: 0 fwd flagged, 1 bwd flagged, 2 fwd max mismatch (float bits), 3 bwd max mismatch bits(hi) ..
     double *Xpart;           // [n_slabs][Mp*Mp]
     double *Rpart;           // [n_slabs][n_eig][Mp*Mp]
@@ -146,7 +147,7 @@ int resident_warps_mma(int n_sm, int Mp);
 void set_fwd_cached_keys(int n);
 void set_chunks_per_warp(int g);
 bool mma_forward_pays(int n_chunks, int n_sm, int Mp);
-void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol, cudaStream_t st);
+void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
