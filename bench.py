@@ -305,8 +305,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64 (float alpha_hat storage, as the reference)", "data": "synthetic",
             "config": {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n}, contigs sharded over ranks",
-                       "l2": "per-step working set (alpha_hat + beta vectors, %.1f GB on rank 0) exceeds L2; no flush needed"
-                             % (my_blocks * (4 * M + 8 * M + 10) / 1e9),
+                       "l2": "per-step working set (alpha_hat, beta and u vectors, %.1f GB on rank 0) exceeds L2; no flush needed"
+                             % (my_blocks * (4 * M + 8 * M + 8 * M + 26) / 1e9),
                        "model_inputs": f"tests/golden/model_{cfg}.npz (reference do_dirty_work output)",
                        "one_time_upload_s": upload_s},
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
@@ -314,9 +314,9 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps, "device_ms_per_step": e2e_stats.get("ms_total")},
             "roofline": {"bound": "hbm", "kernel": "k_forward || k_backward (recursions, rank 0)", "achieved": ach, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach / hbm_peak,
-                         # dram__bytes_read+write of k_forward32m + k_backward32m, one launch each (profiles/r1f_summary.md);
+                         # dram__bytes_read+write of k_forward_mma + k_backward_mma, one launch each (profiles/r1h_summary.md);
                          # measured for this workload on one GPU only
-                         "traffic": 8.98e9 if (cfg == "C3" and world == 1) else None, "peak_source": peak_src,
+                         "traffic": 11.80e9 if (cfg == "C3" and world == 1) else None, "peak_source": peak_src,
                          "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms,
                          "kernel_ms_per_step": [round(float(x), 3) for x in ms_rec]},
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
