@@ -490,7 +490,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     else if (ctx->opt_chunk_blocks > 0) Lc = ctx->opt_chunk_blocks;
     else {
         // as many chunks as fit in ONE resident wave of the recursion kernels (a partial second wave would
-        // double the time), but never shorter than the burn-in, which bounds the redundant work by 2x
+        // double the time)
         int target = ctx->opt_target_warps;
         const bool tensor_path = Mp == 32 || Mp == 64 || Mp == 128;
         auto chunks_for = [&](int64_t lc) {
@@ -498,8 +498,12 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             for (int c = 0; c < ctx->C; ++c) n += (ctx->blk_off[c + 1] - ctx->blk_off[c] + lc - 1) / lc;
             return n;
         };
-        auto min_lc_for = [&](int64_t tgt) {   // shortest chunk length (>= burn-in) that needs at most tgt chunks
-            int64_t lo = std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
+        // shortest chunk length that needs at most tgt chunks; the generic path never goes below the burn-in (bounds the
+        // redundant work by 2x), the tensor path lets its cost model decide (a single 10^6-block contig is latency bound:
+        // 4 717 chunks of 212 + 512 steps beat 1 954 chunks of 512 + 512)
+        bool relaxed = tensor_path && ctx->opt_target_warps <= 0;
+        auto min_lc_for = [&](int64_t tgt) {
+            int64_t lo = relaxed ? 64 : std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
             if (chunks_for(lo) <= tgt) hi = lo;
             while (lo < hi) {
                 const int64_t mid = (lo + hi) / 2;
@@ -517,6 +521,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             // CTAs per SM and kernel: measured cost of one chunk step at M = 32 is ~3 750 cycles with one CTA of each
             // kernel on an SM and ~5 460 with two (profiles/r1h), so the shorter schedule wins below ~4 x 10^6 blocks.
             const int per_layer = ctx->n_sm * 32;
+            // inputs too small to fill the warps with 8 chunks each keep the burn-in as the lower bound
+            if (chunks_for(min_lc_for(per_layer)) < ctx->n_sm * 8) relaxed = false;
             const int layers = std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp), ctx->n_sm * 8) / (ctx->n_sm * 4)));
             const double step_cost[3] = {0.0, 3750.0, 5460.0};
             double best = 0.0;
