@@ -110,7 +110,7 @@ struct smcpp_b200_ctx {
     int opt_burn_in = 512;
     int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
     int n_sm = 148;
-    int opt_slab_blocks = 8192;
+    int opt_slab_blocks = 16384;
     // Forward boundaries are compared as FLOAT vectors.  Pass 0 compares a chunk's burn-in state with its neighbour's end
     // state: two float trajectories with different histories, which agree only to the accumulated rounding noise of the
     // chain (they usually merge bit for bit; the tail over ~10^4 boundaries of the benchmark model is 3.1e-7 of the largest

@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                 pp = fma(ac[i], be[i], pp);
             }
             pp = sum_over_r(pp);                                      // p = alpha_l . beta_l   (all lanes take part)
-            const double inv_p = valid ? 1.0 / pp : 0.0;
-            const double inv_cp = valid ? inv_p / (double)o.cn : 0.0; // 1 / (c_l p_l)
+            const double inv_cp = valid ? 1.0 / (pp * (double)o.cn) : 0.0;   // 1 / (c_l p_l): one division per block
+            const double inv_p = inv_cp * (double)o.cn;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 bvv[i] = be[i] * o.e4.v[i] * inv_cp;

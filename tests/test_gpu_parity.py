@@ -192,6 +192,40 @@ def test_fresh_inputs_against_port(M, n, L):
     ctx.close()
 
 
+@pytest.mark.parametrize("spans", [(2, 5, 40), (3,), tuple(range(2, 400))])
+def test_span_sorted_statistics_against_port(spans):
+    """k_stats32e: long runs of equal span (one rank-1 stream per run, weighted once), runs that cross work items (> 4096
+    span>1 blocks per contig) and all-different spans (rank-2 groups), against the port on the same inputs."""
+    M, n, L = 32, 6, 9000
+    rng = np.random.default_rng(len(spans))
+    w = synth.make_workload("fresh", 1, L, M, n, seed0=77)
+    obs = w.contigs[0].copy()
+    big = obs[:, 0] > 1
+    obs[big, 0] = rng.choice(np.asarray(spans, np.int32), size=int(big.sum()))
+    keys = np.unique(obs[:, 1:], axis=0)
+    K = keys.shape[0]
+    base = rng.random((M, M)) ** 4 + np.eye(M) * 50
+    S = base + base.T
+    for _ in range(200):
+        d = S.sum(1)
+        S = S / np.sqrt(d[:, None] * d[None, :])
+    T = (1 - 1e-5) * S + 1e-5 / (M + 1)
+    pi = rng.random(M) + 0.1
+    pi /= pi.sum()
+    E = np.clip(rng.random((K, M)) * 0.9 + 0.05, 1e-3, 1.0)
+    eig_idx = np.array([k for k in range(K) if ((obs[:, 0] > 1) & (obs[:, 1:] == keys[k]).all(1)).any()], np.int32)
+    eig = capi.host_eigensystems(T, E, eig_idx)
+    assert not eig["eig_cplx"].any()
+    ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
+    assert int(big.sum()) > 4096                                     # more than one work item
+    ctx, out = run_ctx([obs], 1, ref, {"chunk_blocks": 512, "burn_in_blocks": 512, "mma_min_chunks": 1})
+    o = port.hmm_estep(obs, ref)
+    assert abs(out["ll"][0] - o["ll"]) <= LL_RTOL * abs(o["ll"])
+    for k in ("xisum", "gamma0", "gamma_sums"):
+        assert relmax(out[k][0], o[k]) <= STAT_RTOL, k
+    ctx.close()
+
+
 @pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_harness did not travel to this box")
 @pytest.mark.parametrize("cfg,scale", [("C1", 1.0), ("C2", 0.05), ("C4", 0.05), ("C5-64", 0.01)])
 def test_baseline_configs_against_live_reference(cfg, scale):
