@@ -157,6 +157,33 @@ int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gam
 int smcpp_b200_set_save_gamma(smcpp_b200_ctx *ctx, int on);
 int smcpp_b200_fetch_gamma(smcpp_b200_ctx *ctx, int contig, double *out /* (L+1)*M */);
 
+/*
+ * Observation pre-processing on the device: the input side of the path.  One handle holds ONE contig's
+ * rows [span, a_1, b_1, nb_1 (, a_2, b_2, nb_2)] on the GPU; every step replaces them, so the `smc++ estimate` chain
+ * (reference smcpp/analysis/analysis.py:60-63) runs device-resident: upload -> thin -> bin -> recode_monomorphic ->
+ * compress -> download (or hand the rows to set_contigs).  Results are bit-identical to the reference's functions.
+ * Replaces:
+ *   obs_thin               thin_data(data, thinning, offset)   reference smcpp/_estimation_tools.pyx:8-84 (including its
+ *                          treatment of full-SFS bases whose a's sum to 2, :60-68)
+ *   obs_bin                bin_observations(contig, w) + process_bin   smcpp/_estimation_tools.pyx:110-172;
+ *                          a[npop] = distinguished lineages per population (contig.a)
+ *   obs_recode_monomorphic RecodeMonomorphic._recode            smcpp/data_filter.py:331-336
+ *   obs_compress           compress_repeated_obs(dataset)       smcpp/estimation_tools.py:51-61
+ * obs_last_ms: device time (CUDA events) of the last step.  No CPU fallback: create() fails without a CUDA device.
+ */
+typedef struct smcpp_b200_obs smcpp_b200_obs;
+int smcpp_b200_obs_create(smcpp_b200_obs **out, int device);
+void smcpp_b200_obs_destroy(smcpp_b200_obs *o);
+const char *smcpp_b200_obs_last_error(const smcpp_b200_obs *o); /* o may be NULL: error of the last failed create() */
+int smcpp_b200_obs_upload(smcpp_b200_obs *o, const int32_t *rows, int64_t n_rows, int npop);
+int smcpp_b200_obs_thin(smcpp_b200_obs *o, int thinning, int offset);
+int smcpp_b200_obs_bin(smcpp_b200_obs *o, const int64_t *a, int64_t w);
+int smcpp_b200_obs_recode_monomorphic(smcpp_b200_obs *o, const int64_t *a);
+int smcpp_b200_obs_compress(smcpp_b200_obs *o);
+int64_t smcpp_b200_obs_rows(const smcpp_b200_obs *o);
+float smcpp_b200_obs_last_ms(const smcpp_b200_obs *o);
+int smcpp_b200_obs_download(smcpp_b200_obs *o, int32_t *rows /* rows() x (1 + 3 npop) */);
+
 /* Diagnostics of the last estep(): see smcpp_b200_stats_t. */
 typedef struct smcpp_b200_stats_t {
     int32_t n_chunks;        /* chunks the contigs were split into */

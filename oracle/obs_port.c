@@ -4,7 +4,7 @@
  *
  * Pinned against the reference itself: tests/golden/make_obs_golden.py runs the reference's Cython functions
  * (smcpp/_estimation_tools.pyx, compiled in a scratch directory) and pure-Python functions on seeded inputs and stores
- * inputs + outputs in tests/golden/obs_pipeline.npz; tests/test_obs_pipeline.py checks this file against them bit for bit.
+ * inputs + outputs in tests/golden/obs/obs_pipeline.npz; tests/test_obs_pipeline.py checks this file against them bit for bit.
  *
  * Rows are int32 [span, a_1, b_1, nb_1 (, a_2, b_2, nb_2)], W = 1 + 3 npop columns.
  */

@@ -45,6 +45,9 @@ SYMBOLS = [
     "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
     "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat", "smcpp_b200_set_save_gamma",
     "smcpp_b200_fetch_gamma",
+    "smcpp_b200_obs_create", "smcpp_b200_obs_destroy", "smcpp_b200_obs_last_error", "smcpp_b200_obs_upload", "smcpp_b200_obs_thin",
+    "smcpp_b200_obs_bin", "smcpp_b200_obs_recode_monomorphic", "smcpp_b200_obs_compress", "smcpp_b200_obs_rows", "smcpp_b200_obs_last_ms",
+    "smcpp_b200_obs_download",
 ]
 
 
@@ -73,6 +76,14 @@ def lib():
         L.smcpp_b200_destroy.argtypes = [ctypes.c_void_p]
         for name in ("smcpp_b200_num_keys", "smcpp_b200_num_eig_keys"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_obs_last_error.restype = ctypes.c_char_p
+        L.smcpp_b200_obs_last_error.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_obs_rows.restype = ctypes.c_int64
+        L.smcpp_b200_obs_rows.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_obs_last_ms.restype = ctypes.c_float
+        L.smcpp_b200_obs_last_ms.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_obs_destroy.restype = None
+        L.smcpp_b200_obs_destroy.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -310,3 +321,71 @@ class Context:
         out = np.empty((L + 1, self.M), np.float32)
         self._check(lib().smcpp_b200_debug_alpha_hat(self._h, ctypes.c_int(contig), ptr(out, c_f32p)), "debug_alpha_hat")
         return out
+
+
+class ObsPipeline:
+    """Device-resident observation pre-processing of ONE contig (include/smcpp_b200.h: smcpp_b200_obs_*): the reference's
+    Thin -> BinObservations -> RecodeMonomorphic -> Compress chain (smcpp/analysis/analysis.py:60-63)."""
+
+    def __init__(self, rows: np.ndarray, device: int = 0):
+        rows = np.ascontiguousarray(rows, np.int32)
+        if rows.ndim != 2 or rows.shape[1] not in (4, 7):
+            raise ValueError("rows must be int32 [L, 1 + 3*npop]")
+        self._h = ctypes.c_void_p()
+        if lib().smcpp_b200_obs_create(ctypes.byref(self._h), ctypes.c_int(device)):
+            raise RuntimeError("smcpp_b200_obs_create: " + lib().smcpp_b200_obs_last_error(None).decode())
+        self.ms = {}
+        self.upload(rows)
+
+    def upload(self, rows: np.ndarray):
+        """(Re)load one contig's rows; device buffers of earlier runs are reused."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        self.npop = (rows.shape[1] - 1) // 3
+        self._check(lib().smcpp_b200_obs_upload(self._h, ptr(rows, c_i32p), ctypes.c_int64(rows.shape[0]), ctypes.c_int(self.npop)), "upload")
+        return self
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"obs_{what}: " + lib().smcpp_b200_obs_last_error(self._h).decode())
+
+    def _done(self, what):
+        self.ms[what] = float(lib().smcpp_b200_obs_last_ms(self._h))
+        return self
+
+    def thin(self, thinning: int, offset: int = 0):
+        self._check(lib().smcpp_b200_obs_thin(self._h, ctypes.c_int(thinning), ctypes.c_int(offset)), "thin")
+        return self._done("thin")
+
+    def bin(self, a, w: int):
+        a = np.ascontiguousarray(a, np.int64)
+        self._check(lib().smcpp_b200_obs_bin(self._h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.c_int64(w)), "bin")
+        return self._done("bin")
+
+    def recode_monomorphic(self, a):
+        a = np.ascontiguousarray(a, np.int64)
+        self._check(lib().smcpp_b200_obs_recode_monomorphic(self._h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "recode_monomorphic")
+        return self._done("recode_monomorphic")
+
+    def compress(self):
+        self._check(lib().smcpp_b200_obs_compress(self._h), "compress")
+        return self._done("compress")
+
+    @property
+    def n_rows(self) -> int:
+        return int(lib().smcpp_b200_obs_rows(self._h))
+
+    def rows(self) -> np.ndarray:
+        out = np.empty((self.n_rows, 1 + 3 * self.npop), np.int32)
+        self._check(lib().smcpp_b200_obs_download(self._h, ptr(out, c_i32p)), "download")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().smcpp_b200_obs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

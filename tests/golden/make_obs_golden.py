@@ -1,4 +1,4 @@
-"""Generates tests/golden/obs_pipeline.npz: seeded raw observation rows and what the REFERENCE makes of them in the
+"""Generates tests/golden/obs/obs_pipeline.npz: seeded raw observation rows and what the REFERENCE makes of them in the
 `smc++ estimate` pre-processing chain (smcpp/analysis/analysis.py:60-63: Thin -> BinObservations -> RecodeMonomorphic
 -> Compress).  Run in the build container only (needs /root/reference):
 
@@ -123,7 +123,7 @@ def main():
         names.append(name)
         print(name, d.shape, "->", thin.shape, "->", binned.shape, "->", comp.shape)
     out["names"] = np.array(names)
-    np.savez_compressed(os.path.join(HERE, "obs_pipeline.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "obs", "obs_pipeline.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,7 @@
 """Input side of the E-step: thin_data -> bin_observations -> RecodeMonomorphic -> compress_repeated_obs.
 
 CPU part: the oracle restatement (oracle/obs_port.c) against what the reference's own functions produced
-(tests/golden/obs_pipeline.npz, made by tests/golden/make_obs_golden.py from the reference's Cython / Python sources).
+(tests/golden/obs/obs_pipeline.npz, made by tests/golden/make_obs_golden.py from the reference's Cython / Python sources).
 GPU part: the CUDA pipeline (smcpp_b200/csrc/obs_pipeline.cu through the C ABI) against the goldens and, on larger fresh
 inputs, against the oracle -- bit for bit (integer work)."""
 import os
@@ -11,7 +11,7 @@ import pytest
 
 from oracle import obsport
 
-GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obs_pipeline.npz"))
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obs", "obs_pipeline.npz"))
 NAMES = [str(x) for x in GOLD["names"]]
 
 
@@ -41,3 +41,87 @@ def test_oracle_invariants():
     comp = obsport.compress_repeated_obs(thin)
     assert comp[:, 0].astype(np.int64).sum() == thin[:, 0].astype(np.int64).sum()
     assert (np.abs(np.diff(comp[:, 1:], axis=0)).sum(axis=1) > 0).all()                    # no two neighbours share a key
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA pipeline through the C ABI
+# ---------------------------------------------------------------------------------------------------------------
+def _raw_rows(rng, L, npop, n, a):
+    """Fresh seeded rows (vectorised twin of make_obs_golden.raw_rows; the oracle is the checker here)."""
+    W = 1 + 3 * npop
+    d = np.zeros((L, W), np.int32)
+    u = rng.random(L)
+    kind = np.select([u < 0.45, u < 0.55, u < 0.62], [0, 1, 2], 3)
+    d[:, 0] = np.select([kind == 0, kind == 1, kind == 2], [rng.geometric(1 / 300.0, L), rng.geometric(1 / 150.0, L), 1], rng.integers(1, 3, L))
+    for p in range(npop):
+        nb = rng.integers(0, n[p] + 1, L)
+        aa = rng.integers(0, a[p] + 1, L)
+        aa = np.where(rng.random(L) < 0.1, -1, aa)
+        bb = (rng.random(L) * (nb + 1)).astype(np.int64)
+        col = 1 + 3 * p
+        d[:, col] = np.select([kind == 0, kind == 1, kind == 2], [0, -1, a[p]], aa)
+        d[:, col + 2] = np.select([kind == 0, kind == 1], [n[p], 0], nb)
+        d[:, col + 1] = np.select([kind == 0, kind == 1, kind == 2], [0, 0, nb], np.where(aa < 0, 0, bb))
+    return d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_pipeline_matches_reference_outputs(name):
+    from smcpp_b200 import capi
+    g, npop, thinning, w = case(name)
+    p = capi.ObsPipeline(g["raw"])
+    assert np.array_equal(p.thin(thinning).rows(), g["thin"])
+    assert np.array_equal(p.bin(g["a"], w).rows(), g["binned"])
+    assert np.array_equal(p.recode_monomorphic(g["a"]).rows(), g["recoded"])
+    assert np.array_equal(p.compress().rows(), g["compressed"])
+    p.close()
+    p = capi.ObsPipeline(g["raw"])
+    assert np.array_equal(p.compress().rows(), g["raw_compressed"])
+    p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("npop,n,a,L,thinning,w,offset", [(1, (10,), (2,), 400_000, 1243, 100, 0), (2, (6, 4), (1, 1), 200_000, 3, 7, 2),
+                                                            (1, (3,), (2,), 150_000, 1, 1000, 0), (1, (8,), (2,), 100_000, 50, 100, 77)])
+def test_gpu_pipeline_against_oracle_on_fresh_inputs(npop, n, a, L, thinning, w, offset):
+    from smcpp_b200 import capi
+    rng = np.random.default_rng(L + thinning)
+    raw = _raw_rows(rng, L, npop, n, a)
+    p = capi.ObsPipeline(raw)
+    thin = obsport.thin_data(raw, thinning, offset)
+    assert np.array_equal(p.thin(thinning, offset).rows(), thin)
+    assert thin[:, 0].astype(np.int64).sum() == raw[:, 0].astype(np.int64).sum()
+    binned = obsport.bin_observations(thin, a, w)
+    assert np.array_equal(p.bin(a, w).rows(), binned)
+    rec = obsport.recode_monomorphic(binned, a)
+    assert np.array_equal(p.recode_monomorphic(a).rows(), rec)
+    assert np.array_equal(p.compress().rows(), obsport.compress_repeated_obs(rec))
+    p.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_feeds_the_estep_context():
+    # the compressed rows are exactly what set_contigs() expects (span > 0, C-contiguous int32)
+    from smcpp_b200 import capi
+    g, npop, thinning, w = case("p1")
+    p = capi.ObsPipeline(g["raw"])
+    rows = p.thin(thinning).bin(g["a"], w).recode_monomorphic(g["a"]).compress().rows()
+    p.close()
+    ctx = capi.Context(0)
+    ctx.set_contigs([rows], npop)
+    assert ctx.total_blocks == rows.shape[0] and (rows[:, 0] > 0).all()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_errors():
+    from smcpp_b200 import capi
+    with pytest.raises(ValueError):
+        capi.ObsPipeline(np.zeros((4, 5), np.int32))
+    p = capi.ObsPipeline(np.array([[3, 0, 0, 2]], np.int32))
+    with pytest.raises(RuntimeError, match="thinning"):
+        p.thin(0)
+    with pytest.raises(RuntimeError, match="w >= 1"):
+        p.bin([2], 0)
+    p.close()
