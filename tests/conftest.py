@@ -16,6 +16,7 @@ def pytest_configure(config):
 def _built():
     """The product library and the oracle port are built in-tree (no-ops when up to date)."""
     from smcpp_b200 import capi
-    from oracle import port
+    from oracle import obsport, port
     capi.build()
     port.build()
+    obsport.build()

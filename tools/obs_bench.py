@@ -5,7 +5,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from smcpp_b200 import capi
-from oracle import obsport
 from test_obs_pipeline import _raw_rows
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
@@ -29,6 +28,9 @@ by = {"thin": 4 * W * (sizes[0] + sizes[1]), "bin": 4 * W * (sizes[1] + sizes[2]
 res["steps"] = {k: {"ms": ms[k], "alg_GBps": by[k] / ms[k] / 1e6} for k in ms}
 res["rows"] = sizes
 res["total_ms"] = sum(ms.values())
+# CPU baseline (measurement only, like bench.py's cpu_baseline leg): the oracle's sequential restatement of the reference
+# functions, one host core, on a bounded sample of the same rows
+from oracle import obsport
 sample = raw[:min(L, 2_000_000)]
 t0 = time.perf_counter()
 t = obsport.thin_data(sample, thinning); b = obsport.bin_observations(t, a, w); r = obsport.recode_monomorphic(b, a); c = obsport.compress_repeated_obs(r)
