@@ -74,7 +74,12 @@ __device__ __forceinline__ void store_acc(double *sm, const double (&acc)[4][4][
         }
 }
 
-__global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, Work w)
+// gs_in_smem: the per-key gamma sums of the slab ([K][32] doubles) live in shared memory while K <= kS32MaxKeysSmem;
+// data sets with more distinct keys (two-population full-SFS data reach ~10^3) accumulate them straight in the slab's
+// output rows in global memory -- same code, same order, L2 instead of shared memory.
+constexpr int kS32MaxKeysSmem = 288;
+
+__global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, Work w, int gs_in_smem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = m.K, NE = m.n_eig;
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
     const int32_t *seg = p.seg + (size_t)slab * (NE + 2);   // [dense | eig 0 | eig 1 | ... ] offsets into perm
 
     double *tiles = reinterpret_cast<double *>(smem_raw);                   // [kS32Warps][32*33]
-    double *gs = tiles + (size_t)kS32Warps * 32 * 33;                       // [K][32]
-    double *bnd = gs + (size_t)K * 32;                                      // [kS32Warps][2][32] boundary key sums
+    double *gs_s = tiles + (size_t)kS32Warps * 32 * 33;                     // [K][32] (only when gs_in_smem)
+    double *gs = gs_in_smem ? gs_s : w.gspart + (size_t)slab * K * 32;
+    double *bnd = gs_s + (size_t)(gs_in_smem ? K : 0) * 32;                 // [kS32Warps][2][32] boundary key sums
     double *dred = bnd + (size_t)kS32Warps * 2 * 32;                        // [kS32Warps][32]
     int *bkey = reinterpret_cast<int *>(dred + (size_t)kS32Warps * 32);     // [kS32Warps][2]
 
@@ -234,8 +240,10 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
                 }
         }
         __syncthreads();
-        double *gp = w.gspart + (size_t)slab * K * 32;
-        for (int x = tid; x < K * 32; x += kS32Warps * 32) gp[x] = gs[x];
+        if (gs_in_smem) {
+            double *gp = w.gspart + (size_t)slab * K * 32;
+            for (int x = tid; x < K * 32; x += kS32Warps * 32) gp[x] = gs[x];
+        }
         __syncthreads();
     }
 
@@ -397,7 +405,8 @@ __global__ void __launch_bounds__(kSEWarps * 32, 2) k_stats32e(Model m, Plan p, 
 
 size_t stats32_smem_bytes(const Model &m)
 {
-    return ((size_t)kS32Warps * 32 * 33 + (size_t)m.K * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32) * sizeof(double) +
+    const size_t kk = m.K <= kS32MaxKeysSmem ? m.K : 0;
+    return ((size_t)kS32Warps * 32 * 33 + kk * 32 + (size_t)kS32Warps * 2 * 32 + (size_t)kS32Warps * 32) * sizeof(double) +
            (size_t)kS32Warps * 2 * sizeof(int);
 }
 
@@ -409,7 +418,7 @@ void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t s
         cudaFuncSetAttribute(k_stats32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w);
+    k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w, m.K <= kS32MaxKeysSmem ? 1 : 0);
     if (p.n_items > 0) {
         const size_t smem_e = ((size_t)kSEWarps * 32 * 33 + (size_t)kSEWarps * 32) * sizeof(double);
         static bool configured_e = false;

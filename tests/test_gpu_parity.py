@@ -226,6 +226,37 @@ def test_span_sorted_statistics_against_port(spans):
     ctx.close()
 
 
+def test_many_keys_two_populations():
+    """More distinct observation keys than k_stats32 keeps in shared memory (two-population full-SFS data): the per-key
+    gamma sums then accumulate in global memory."""
+    M, L = 32, 20000
+    rng = np.random.default_rng(4242)
+    w = synth.make_workload("fresh", 1, L, M, (14, 14), npop=2, seed0=31)
+    obs = w.contigs[0]
+    keys = np.unique(obs[:, 1:], axis=0)
+    K = keys.shape[0]
+    assert K > 288
+    base = rng.random((M, M)) ** 4 + np.eye(M) * 50
+    S = base + base.T
+    for _ in range(200):
+        d = S.sum(1)
+        S = S / np.sqrt(d[:, None] * d[None, :])
+    T = (1 - 1e-5) * S + 1e-5 / (M + 1)
+    pi = rng.random(M) + 0.1
+    pi /= pi.sum()
+    E = np.clip(rng.random((K, M)) * 0.9 + 0.05, 1e-3, 1.0)
+    eig_idx = np.array([k for k in range(K) if ((obs[:, 0] > 1) & (obs[:, 1:] == keys[k]).all(1)).any()], np.int32)
+    eig = capi.host_eigensystems(T, E, eig_idx)
+    ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
+    ctx, out = run_ctx([obs], 2, ref, {"chunk_blocks": 1024, "burn_in_blocks": 512, "mma_min_chunks": 1})
+    o = port.hmm_estep(obs, ref)
+    assert abs(out["ll"][0] - o["ll"]) <= LL_RTOL * abs(o["ll"])
+    for k in ("xisum", "gamma0", "gamma_sums"):
+        assert relmax(out[k][0], o[k]) <= STAT_RTOL, k
+    assert np.array_equal(out["key_present"][0], (o["gamma_sums"] != 0).any(1) | out["key_present"][0].astype(bool))
+    ctx.close()
+
+
 @pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_harness did not travel to this box")
 @pytest.mark.parametrize("cfg,scale", [("C1", 1.0), ("C2", 0.05), ("C4", 0.05), ("C5-64", 0.01)])
 def test_baseline_configs_against_live_reference(cfg, scale):
