@@ -36,7 +36,7 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device);
 void smcpp_b200_destroy(smcpp_b200_ctx *ctx);
 const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx); /* ctx may be NULL: error of the last failed create() */
 
-/* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks", "target_warps", "slab_blocks", "fwd_tol",
+/* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks" (both passes), "burn_in_blocks_forward", "target_warps", "slab_blocks", "fwd_tol",
  * "fwd_tol_burn_in", "bwd_tol", "max_sweeps", "force_sequential", "mma_min_chunks", "force_mma_forward", "chunks_per_warp",
  * "fwd_cached_keys"} (the last two are process-wide and exist for tests / experiments).
  * Returns non-zero for an unknown name. */

@@ -108,6 +108,10 @@ struct smcpp_b200_ctx {
     // ---- options
     int opt_chunk_blocks = 0;       // 0 = auto
     int opt_burn_in = 512;
+    // The forward pass only has to reach the float noise floor (accepted at 1e-6), the backward pass 1e-10 in fp64: at the
+    // benchmark model's contraction (~10x per 43 blocks) that is ~280 resp. ~430 blocks from an arbitrary start.
+    int opt_burn_in_fwd = 384;
+    int burn_in_fwd_adapt = 0;
     int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
     int n_sm = 148;
     int opt_slab_blocks = 16384;
@@ -172,6 +176,7 @@ struct smcpp_b200_ctx {
         Plan p;
         p.n_contigs = C; p.n_chunks = n_chunks; p.n_slabs = n_slabs;
         p.chunk_blocks = plan_Lc; p.burn_in = plan_burn; p.slab_blocks = plan_slab;
+        p.burn_in_fwd = std::max(0, std::min(plan_burn, opt_burn_in_fwd + burn_in_fwd_adapt));
         p.total_blocks = total;
         p.span = d_span.p; p.kcode = d_key.p; p.span_id = d_span_id.p;
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
@@ -288,7 +293,8 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     if (!ctx || !name) return 1;
     std::string n(name);
     if (n == "chunk_blocks") ctx->opt_chunk_blocks = (int)value;
-    else if (n == "burn_in_blocks") { ctx->opt_burn_in = (int)value; ctx->burn_in_adapt = 0; }
+    else if (n == "burn_in_blocks") { ctx->opt_burn_in = (int)value; ctx->burn_in_adapt = 0; ctx->opt_burn_in_fwd = (int)value; ctx->burn_in_fwd_adapt = 0; }
+    else if (n == "burn_in_blocks_forward") { ctx->opt_burn_in_fwd = (int)value; ctx->burn_in_fwd_adapt = 0; }
     else if (n == "target_warps") ctx->opt_target_warps = std::max(0, (int)value);
     else if (n == "slab_blocks") ctx->opt_slab_blocks = std::max(32, (int)value);
     else if (n == "fwd_tol") ctx->opt_fwd_tol = value;
@@ -853,7 +859,13 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     if ((fwd_redone || bwd_redone) && !ctx->opt_force_sequential) {
         const int cur = ctx->opt_burn_in + ctx->burn_in_adapt;
         const bool near_miss = fwd_mm <= 30.f * (float)ctx->opt_fwd_tol0 && bwd_mm <= 30.f * (float)ctx->opt_bwd_tol;
-        ctx->burn_in_adapt += near_miss ? 128 : std::max(cur, 256);
+        if (near_miss) {
+            if (fwd_redone) ctx->burn_in_fwd_adapt += 128;
+            if (bwd_redone) ctx->burn_in_adapt += 128;
+        } else {
+            ctx->burn_in_adapt += std::max(cur, 256);
+            ctx->burn_in_fwd_adapt += std::max(ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt, 256);
+        }
     }
     cudaEventRecord(ctx->ev[2], ctx->st);
     launch_stats(m, p, w, ctx->st);

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
     float x[R];
     int b0;
     if (pass == 0) {
-        b0 = s - p.burn_in;
+        b0 = s - p.burn_in_fwd;
         if (b0 < 0) b0 = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = (float)m.pi[lane + 32 * r];  // src/hmm.cpp:59

@@ -61,7 +61,8 @@ struct Model {
 // Static per-dataset layout (set_contigs) + per-plan chunking.
 struct Plan {
     int n_contigs, n_chunks, n_slabs;
-    int chunk_blocks, burn_in, slab_blocks;
+    int chunk_blocks, burn_in, slab_blocks;   // burn_in: backward recursion (fp64 beta, verified to 1e-10)
+    int burn_in_fwd;                          // forward recursion (float alpha_hat, verified to the float noise floor): shorter
     int64_t total_blocks;
     // per block (concatenated over contigs)
     const int32_t *span;     // [total]

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_forward32(Model m, Plan p, Wo
     float x;
     int b0;
     if (pass == 0) {
-        b0 = s - p.burn_in;
+        b0 = s - p.burn_in_fwd;
         if (b0 < 0) b0 = 0;
         x = (float)m.pi[lane];
     } else {

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
     const int64_t g0 = p.blk_off[t];
     const int bend = s + len;
     float *acol = w.alpha + (p.col_off[t] + (int64_t)(cc - p.chunk_off[t]) * (p.chunk_blocks + 1)) * MP;
-    int cur = s - p.burn_in;
+    int cur = s - p.burn_in_fwd;
     if (cur < 0) cur = 0;
 
     float x[NI];
