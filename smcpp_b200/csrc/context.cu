@@ -886,7 +886,8 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     }
     launch_finalize(m, p, w, ctx->st);
     cudaEventRecord(ctx->ev[4], ctx->st);
-    ctx->stats.kernel_launches += 4;
+    // statistics: k_stats32 (+ k_stats32e when there are span>1 items) or the generic k_stats; finalize: 3 kernels
+    ctx->stats.kernel_launches += ((m.Mp == 32 && p.n_items > 0) ? 2 : 1) + 3;
     CU(cudaGetLastError());
     ctx->stats.n_chunks = p.n_chunks;
     ctx->stats.chunk_blocks = p.chunk_blocks;
