@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 
 #include "../../include/smcpp_b200.h"
@@ -89,14 +90,32 @@ __device__ __forceinline__ int64_t last_le(const int64_t *v, int64_t lo, int64_t
     }
     return lo;
 }
-// The outputs of a thread block are consecutive, so their source rows form one short range: two threads search the whole
-// array for the block's first and last key, every thread then searches only that range (a handful of cached steps
-// instead of ~25 scattered ones per output row).
-__device__ __forceinline__ void block_range(const int64_t *v, int64_t n, int64_t key_first, int64_t key_last, int64_t *s_range)
+// The outputs of a thread block are consecutive, so their source rows form one short range.  A partition pass finds the
+// first source row of every 256-output chunk (one thread per chunk, all searches in parallel); the main kernels then stage
+// the chunk's slice of the scanned array in shared memory and every thread searches it there (merge-path style).
+constexpr int kChunk = 256;        // outputs per thread block iteration (= block size)
+constexpr int kStage = 2048;       // slice entries staged in shared memory; longer slices are searched in global memory
+__global__ void k_partition(const int64_t *v, int64_t n, int64_t n_chunks, int64_t step, int64_t *part)
 {
-    if (threadIdx.x == 0) s_range[0] = last_le(v, 0, n - 1, key_first);
-    if (threadIdx.x == 32) s_range[1] = last_le(v, 0, n - 1, key_last);
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c <= n_chunks; c += (int64_t)gridDim.x * blockDim.x)
+        part[c] = c < n_chunks ? last_le(v, 0, n - 1, c * step) : n - 1;
+}
+struct Slice { int64_t lo, hi; bool staged; };
+__device__ __forceinline__ Slice stage_slice(const int64_t *v, const int64_t *part, int64_t c, int64_t *s_v)
+{
+    Slice sl;
+    sl.lo = part[c];
+    sl.hi = part[c + 1];
+    sl.staged = sl.hi - sl.lo < kStage;
+    __syncthreads();                                   // the previous iteration's readers are done with s_v
+    if (sl.staged)
+        for (int64_t i = threadIdx.x; i <= sl.hi - sl.lo; i += blockDim.x) s_v[i] = v[sl.lo + i];
     __syncthreads();
+    return sl;
+}
+__device__ __forceinline__ int64_t slice_last_le(const Slice &sl, const int64_t *v, const int64_t *s_v, int64_t key)
+{
+    return sl.staged ? sl.lo + last_le(s_v, 0, sl.hi - sl.lo, key) : last_le(v, sl.lo, sl.hi, key);
 }
 
 // ---- thin_data ---------------------------------------------------------------------------------------------
@@ -126,19 +145,17 @@ __global__ void k_thin_count(const int32_t *rows, const int64_t *pos, int64_t n,
 }
 
 // one thread per output row: find its input row (binary search in the scanned counts), then its piece
-__global__ void k_thin_write(const int32_t *rows, const int64_t *pos, const int64_t *off, int64_t n, int64_t n_out, Params P,
-                             int64_t thinning, int64_t offset, int32_t *out)
+__global__ void __launch_bounds__(kChunk) k_thin_write(const int32_t *rows, const int64_t *pos, const int64_t *off, const int64_t *part, int64_t n,
+                                                       int64_t n_out, Params P, int64_t thinning, int64_t offset, int32_t *out)
 {
     const int W = P.W;
-    __shared__ int64_t s_range[2];
-    for (int64_t t0 = blockIdx.x * (int64_t)blockDim.x; t0 < n_out; t0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t_last = t0 + blockDim.x - 1 < n_out ? t0 + blockDim.x - 1 : n_out - 1;
-        block_range(off, n, t0, t_last, s_range);
-        const int64_t t = t0 + threadIdx.x;
-        const int64_t jlo = s_range[0], jhi = s_range[1];
-        __syncthreads();
+    __shared__ int64_t s_v[kStage];
+    const int64_t n_chunks = (n_out + kChunk - 1) / kChunk;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const Slice sl = stage_slice(off, part, c, s_v);
+        const int64_t t = c * kChunk + threadIdx.x;
         if (t >= n_out) continue;
-        const int64_t j = last_le(off, jlo, jhi, t), u = t - off[j];   // last j with off[j] <= t
+        const int64_t j = slice_last_le(sl, off, s_v, t), u = t - off[j];   // last j with off[j] <= t
         const Row row = load_row(rows, j, W);
         const int64_t s = row.v[0];
         const ThinRow tr = thin_row(pos[j], s, thinning, offset);
@@ -168,19 +185,18 @@ __global__ void k_thin_write(const int32_t *rows, const int64_t *pos, const int6
 }
 
 // ---- bin_observations (+ RecodeMonomorphic fused on request) --------------------------------------------------
-__global__ void k_bin(const int32_t *rows, const int64_t *pos, int64_t n, int64_t total, int64_t n_bins, Params P, int64_t w, int32_t *out)
+__global__ void __launch_bounds__(kChunk) k_bin(const int32_t *rows, const int64_t *pos, const int64_t *part, int64_t n, int64_t total, int64_t n_bins,
+                                                Params P, int64_t w, int32_t *out)
 {
     const int W = P.W;
-    __shared__ int64_t s_range[2];
-    for (int64_t m0 = blockIdx.x * (int64_t)blockDim.x; m0 < n_bins; m0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m_last = m0 + blockDim.x - 1 < n_bins ? m0 + blockDim.x - 1 : n_bins - 1;
-        block_range(pos, n, m0 * w, m_last * w, s_range);
-        const int64_t m = m0 + threadIdx.x;
-        const int64_t jlo = s_range[0], jhi = s_range[1];
-        __syncthreads();
+    __shared__ int64_t s_v[kStage];
+    const int64_t n_chunks = (n_bins + kChunk - 1) / kChunk;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const Slice sl = stage_slice(pos, part, c, s_v);
+        const int64_t m = c * kChunk + threadIdx.x;
         if (m >= n_bins) continue;
         const int64_t b0 = m * w, b1 = (m + 1) * w < total ? (m + 1) * w : total;
-        const int64_t lo = last_le(pos, jlo, jhi, b0);               // last row that starts at or before b0
+        const int64_t lo = slice_last_le(sl, pos, s_v, b0);           // last row that starts at or before b0
         int max_sample = -2;
         Row best = load_row(rows, lo, W);
         for (int64_t q = lo; q < n && pos[q] < b1; ++q) {             // rows that overlap [b0, b1) (process_bin skips empty parts)
@@ -265,7 +281,7 @@ struct smcpp_b200_obs {
     int npop = 0, W = 0;
     int64_t n = 0;                     // rows currently held
     Buf<int32_t> rows, rows2;          // current rows / output of the running step (swapped)
-    Buf<int64_t> a64, b64, c64;        // spans / counts / flags, their scans, run starts
+    Buf<int64_t> a64, b64, c64, part;  // spans / counts / flags, their scans, run starts; chunk partition
     Buf<unsigned char> cub_tmp;
     int64_t *h_pin = nullptr;          // 2 pinned int64 for scalar read-backs
     float last_ms = 0.f;               // device time of the last step (CUDA events)
@@ -355,7 +371,7 @@ void smcpp_b200_obs_destroy(smcpp_b200_obs *o)
     if (!o) return;
     cudaSetDevice(o->device);
     cudaStreamSynchronize(o->st);
-    o->rows.release(); o->rows2.release(); o->a64.release(); o->b64.release(); o->c64.release(); o->cub_tmp.release();
+    o->rows.release(); o->rows2.release(); o->a64.release(); o->b64.release(); o->c64.release(); o->part.release(); o->cub_tmp.release();
     if (o->h_pin) cudaFreeHost(o->h_pin);
     if (o->e0) cudaEventDestroy(o->e0);
     if (o->e1) cudaEventDestroy(o->e1);
@@ -405,8 +421,13 @@ int smcpp_b200_obs_thin(smcpp_b200_obs *o, int thinning, int offset)
     if (scan_total(o, o->a64.p, o->c64.p, o->n, &n_out)) return 1;
     if (n_out > 0x7fffffffLL) { o->err = "obs_thin: result exceeds 2^31 - 1 rows"; return 1; }
     OCU(o->rows2.ensure((size_t)n_out * o->W));
-    k_thin_write<<<grid_for(n_out), 256, 0, o->st>>>(o->rows.p, o->b64.p, o->c64.p, o->n, n_out, make_params(o, nullptr), thinning, offset,
-                                                       o->rows2.p);
+    {
+        const int64_t n_chunks = (n_out + kChunk - 1) / kChunk;
+        OCU(o->part.ensure(n_chunks + 1));
+        k_partition<<<grid_for(n_chunks + 1), 256, 0, o->st>>>(o->c64.p, o->n, n_chunks, kChunk, o->part.p);
+        k_thin_write<<<(int)std::min<int64_t>(n_chunks, 148 * 32), kChunk, 0, o->st>>>(o->rows.p, o->b64.p, o->c64.p, o->part.p, o->n, n_out,
+                                                                                       make_params(o, nullptr), thinning, offset, o->rows2.p);
+    }
     cudaEventRecord(o->e1, o->st);
     OCU(cudaStreamSynchronize(o->st));
     OCU(cudaGetLastError());
@@ -426,7 +447,13 @@ int smcpp_b200_obs_bin(smcpp_b200_obs *o, const int64_t *a, int64_t w)
     if (positions(o, &total)) return 1;
     const int64_t n_bins = (total + w - 1) / w;
     OCU(o->rows2.ensure((size_t)n_bins * o->W));
-    k_bin<<<grid_for(n_bins), 256, 0, o->st>>>(o->rows.p, o->b64.p, o->n, total, n_bins, make_params(o, a), w, o->rows2.p);
+    {
+        const int64_t n_chunks = (n_bins + kChunk - 1) / kChunk;
+        OCU(o->part.ensure(n_chunks + 1));
+        k_partition<<<grid_for(n_chunks + 1), 256, 0, o->st>>>(o->b64.p, o->n, n_chunks, (int64_t)kChunk * w, o->part.p);
+        k_bin<<<(int)std::min<int64_t>(n_chunks, 148 * 32), kChunk, 0, o->st>>>(o->rows.p, o->b64.p, o->part.p, o->n, total, n_bins,
+                                                                                make_params(o, a), w, o->rows2.p);
+    }
     cudaEventRecord(o->e1, o->st);
     OCU(cudaStreamSynchronize(o->st));
     OCU(cudaGetLastError());
