@@ -118,9 +118,12 @@ struct smcpp_b200_ctx {
     // Forward boundaries are compared as FLOAT vectors.  Pass 0 compares a chunk's burn-in state with its neighbour's end
     // state: two float trajectories with different histories, which agree only to the accumulated rounding noise of the
     // chain (they usually merge bit for bit; the tail over ~10^4 boundaries of the benchmark model is 3.1e-7 of the largest
-    // entry at the default burn-in and still 2.3e-7 at 768 blocks) -- accepted up to 1e-6 (~16 float ulps).  A repair sweep
-    // CONTINUES the neighbour's trajectory, so there the tighter 4e-7 applies and is reached.
-    double opt_fwd_tol = 4e-7, opt_fwd_tol0 = 1e-6, opt_bwd_tol = 1e-10;
+    // entry at the default burn-in and still 2.3e-7 at 768 blocks) -- accepted up to 1e-6 (~16 float ulps); such deviations
+    // are independent from chunk to chunk and average out of the statistics (measured 2e-9).  A repair sweep CONTINUES the
+    // neighbour's trajectory, so there agreement is exact once the neighbour is final, and anything less is a systematic,
+    // same-signed contraction error that adds up over chunks (fuzz case: 157 chunks of 16 blocks without burn-in, 4e-7 per
+    // boundary -> 1.9e-7 in xi): re-run chunks are held to bitwise equality (reached after at most #chunks sweeps).
+    double opt_fwd_tol = 0.0, opt_fwd_tol0 = 1e-6, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
     int opt_force_sequential = 0;
     int opt_force_mma_forward = 0;  // tests: take the tensor-path forward kernel even where mma_forward_pays() says no

@@ -155,7 +155,7 @@ def test_zero_burn_in_degenerates_to_sequential_sweeps():
     seq = port.hmm_estep(g.contigs[0][:400], g.ref)
     st = ctx.stats()
     assert st["fwd_sweeps"] > 1 and st["bwd_sweeps"] > 1      # every boundary starts wrong and is repaired
-    # sweeps stop once every boundary agrees to the float noise floor (fwd_tol), not bit for bit
+    # re-run chunks are swept until their boundaries agree bit for bit (fwd_tol = 0), the backward pass to 1e-10
     assert abs(out["ll"][0] - seq["ll"]) <= LL_RTOL * abs(seq["ll"])
     assert relmax(out["xisum"][0], seq["xisum"]) <= STAT_RTOL
     ctx.close()
@@ -387,3 +387,22 @@ def test_inference_manager_gammas_with_save_gamma():
         assert gam[c].shape == (ref["pi"].shape[0], obs.shape[0] + 1)      # M x (L+1), as _PyInferenceManager.gammas
         span = np.concatenate([[1], obs[:, 0]])[:, None]
         assert relmax(gam[c].T / span, o["gamma_full"] / span) <= 1e-6
+
+
+def test_randomised_parity_sweep():
+    """tools/fuzz_parity.py: random small data sets (one/two populations, M = 1..64, degenerate span patterns, contigs of a
+    single block) under random planner options, against the port."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                               "tools", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for i in range(40):
+        w, desc = fz.one_case(rng, i)
+        if w is not None:
+            assert w <= 1.0, desc
+            worst = max(worst, w)
+    assert worst > 0.0
