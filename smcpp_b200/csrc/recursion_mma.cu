@@ -89,17 +89,6 @@ __device__ __forceinline__ void gemv_hot(const double (&R)[NF], const double *S,
     else gemv8<NS, false>(Gm, v, y, lane);
 }
 
-struct float8 { float v[8]; };
-// one 256-bit read-only load (sm_100: LDG.E.256): 8 consecutive floats, 32-byte aligned
-__device__ __forceinline__ float8 ldg256(const float *p)
-{
-    float8 r;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-        : "l"(p));
-    return r;
-}
-
 // ---- packed float pairs (sm_100 FFMA2): the span-1 float GEMV must round the product and the sum separately (the
 // reference's Eigen GEMV is compiled without FMA), which costs an FMUL and an FADD per element.  Two exact identities
 // let one packed instruction do each for TWO elements without ever fusing them:
@@ -165,22 +154,6 @@ __device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32
             }
         }
     }
-}
-
-// Eigen's float sum() order for exactly MPX = 32 NS aligned coefficients in shared memory (see eigen_sum_f32), unrolled
-template <int MPX>
-__device__ __forceinline__ float eigen_sum_f32_full(const float *v)
-{
-    const float4 *v4 = reinterpret_cast<const float4 *>(v);
-    float4 p0 = v4[0], p1 = v4[1];
-#pragma unroll
-    for (int qq = 1; qq < MPX / 8; ++qq) {
-        const float4 a = v4[2 * qq], b = v4[2 * qq + 1];
-        p0.x = __fadd_rn(p0.x, a.x); p0.y = __fadd_rn(p0.y, a.y); p0.z = __fadd_rn(p0.z, a.z); p0.w = __fadd_rn(p0.w, a.w);
-        p1.x = __fadd_rn(p1.x, b.x); p1.y = __fadd_rn(p1.y, b.y); p1.z = __fadd_rn(p1.z, b.z); p1.w = __fadd_rn(p1.w, b.w);
-    }
-    p0.x = __fadd_rn(p0.x, p1.x); p0.y = __fadd_rn(p0.y, p1.y); p0.z = __fadd_rn(p0.z, p1.z); p0.w = __fadd_rn(p0.w, p1.w);
-    return __fadd_rn(__fadd_rn(p0.x, p0.z), __fadd_rn(p0.y, p0.w));
 }
 
 __device__ __forceinline__ double group_sum(double v)   // over the 4 lanes of a chunk
@@ -427,7 +400,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 #pragma unroll
             for (int idx = 0; idx < NI / 2; ++idx) unpack2(y2[idx], y[2 * idx], y[2 * idx + 1]);
             if (M == MP) {
-                // Eigen's sum() order for 32 NS aligned floats (eigen_sum_f32_full: packets p0 / p1 accumulate the
+                // Eigen's sum() order for 32 NS aligned floats (device_utils.cuh: eigen_sum_f32; packets p0 / p1 accumulate the
                 // coefficients = c and = 4 + c (mod 8), then p0 + p1, then (x + z) + (y + w)) without a trip through shared
                 // memory: lane q holds exactly the coefficients = 2q, 2q + 1 (mod 8), in ascending order, so its two
                 // chains are p0.x/p0.y (q = 0), p0.z/p0.w (q = 1), p1.x/p1.y (q = 2), p1.z/p1.w (q = 3); the rest is
