@@ -114,7 +114,7 @@ struct smcpp_b200_ctx {
     int burn_in_fwd_adapt = 0;
     int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
     int n_sm = 148;
-    int opt_slab_blocks = 16384;
+    int opt_slab_blocks = 0;        // 0 = auto: up to 16384 blocks, but at least ~8 slabs per SM
     // Forward boundaries are compared as FLOAT vectors.  Pass 0 compares a chunk's burn-in state with its neighbour's end
     // state: two float trajectories with different histories, which agree only to the accumulated rounding noise of the
     // chain (they usually merge bit for bit; the tail over ~10^4 boundaries of the benchmark model is 3.1e-7 of the largest
@@ -299,7 +299,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "burn_in_blocks") { ctx->opt_burn_in = (int)value; ctx->burn_in_adapt = 0; ctx->opt_burn_in_fwd = (int)value; ctx->burn_in_fwd_adapt = 0; }
     else if (n == "burn_in_blocks_forward") { ctx->opt_burn_in_fwd = (int)value; ctx->burn_in_fwd_adapt = 0; }
     else if (n == "target_warps") ctx->opt_target_warps = std::max(0, (int)value);
-    else if (n == "slab_blocks") ctx->opt_slab_blocks = std::max(32, (int)value);
+    else if (n == "slab_blocks") ctx->opt_slab_blocks = value > 0 ? std::max(32, (int)value) : 0;
     else if (n == "fwd_tol") ctx->opt_fwd_tol = value;
     else if (n == "fwd_tol_burn_in") ctx->opt_fwd_tol0 = value;
     else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
@@ -510,7 +510,9 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         // shortest chunk length that needs at most tgt chunks; the generic path never goes below the burn-in (bounds the
         // redundant work by 2x), the tensor path lets its cost model decide (a single 10^6-block contig is latency bound:
         // 4 717 chunks of 212 + 512 steps beat 1 954 chunks of 512 + 512)
-        bool relaxed = tensor_path && ctx->opt_target_warps <= 0;
+        // (M <= 64 only: at 128 states a chunk step is throughput bound and the redundant burn-in steps cost what they
+        // weigh -- measured 53.8 ms with the bound, 69.9 ms without)
+        bool relaxed = tensor_path && Mp <= 64 && ctx->opt_target_warps <= 0;
         auto min_lc_for = [&](int64_t tgt) {
             int64_t lo = relaxed ? 64 : std::max(burn, 64), hi = std::max<int64_t>(maxL, lo);
             if (chunks_for(lo) <= tgt) hi = lo;
@@ -547,7 +549,13 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     }
     if (Lc > maxL) Lc = (int)maxL;
     if (Lc < 1) Lc = 1;
-    const int slab = ctx->opt_slab_blocks;
+    // statistics slabs: large slabs amortise the per-slab epilogue (16384 blocks: -0.1 ms on C3), small inputs still
+    // need enough slabs to fill the GPU (a single 10^6-block contig would get 61)
+    int slab = ctx->opt_slab_blocks;
+    if (slab <= 0) {
+        const int64_t per = ctx->total / ((int64_t)ctx->n_sm * 8);
+        slab = (int)std::min<int64_t>(16384, std::max<int64_t>(2048, (per / 32) * 32));
+    }
     const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M;
     ctx->plan_burn = burn;
     if (same) return 0;
