@@ -625,6 +625,9 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     std::vector<int32_t> it_len, it_contig, it_eig, it_off;
     if (Mp == 32 && NEp > 0) {
         const int NS = (int)ctx->span_list.size();
+        // item size: up to kItemBlocks, but small inputs still get ~4 items per SM (about half of the blocks have span > 1)
+        const int64_t item_blocks =
+            std::min<int64_t>(kItemBlocks, std::max<int64_t>(512, ((ctx->total / 2 / ((int64_t)ctx->n_sm * 4)) / 32) * 32));
         std::vector<int64_t> cnt;
         for (int c = 0; c < C; ++c) {
             const int64_t g0 = ctx->blk_off[c], L = ctx->blk_off[c + 1] - g0;
@@ -649,9 +652,9 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             for (int e = 0; e < NEp; ++e) {
                 const int64_t hi = cnt[(size_t)e * NS + NS - 1];
                 it_off.push_back((int32_t)it_len.size());
-                for (int64_t a = lo; a < hi; a += kItemBlocks) {
+                for (int64_t a = lo; a < hi; a += item_blocks) {
                     it_start.push_back((int64_t)base + a);
-                    it_len.push_back((int32_t)std::min<int64_t>(kItemBlocks, hi - a));
+                    it_len.push_back((int32_t)std::min<int64_t>(item_blocks, hi - a));
                     it_contig.push_back(c);
                     it_eig.push_back(e);
                 }
