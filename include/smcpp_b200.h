@@ -180,6 +180,16 @@ int smcpp_b200_obs_thin(smcpp_b200_obs *o, int thinning, int offset);
 int smcpp_b200_obs_bin(smcpp_b200_obs *o, const int64_t *a, int64_t w);
 int smcpp_b200_obs_recode_monomorphic(smcpp_b200_obs *o, const int64_t *a);
 int smcpp_b200_obs_compress(smcpp_b200_obs *o);
+/* The front of the chain (reference smcpp/analysis/base.py:50-52): RecodeNonseg(cutoff) -> Compress -> BreakLongSpans.
+ *   obs_recode_nonseg      recode_nonseg(contig, cutoff) with a cutoff given   smcpp/estimation_tools.py:88-114
+ *   obs_break_long_spans   break_long_spans(contig, span_cutoff)              smcpp/estimation_tools.py:117-167: cuts the contig
+ *                          at long missing rows; the pieces (each led by a one-base missing row) stay on the device one
+ *                          after the other; piece_offsets returns n_pieces + 1 row offsets, select_piece makes the rows
+ *                          [row_begin, row_end) of the broken array (normally one piece's range) the handle's current rows. */
+int smcpp_b200_obs_recode_nonseg(smcpp_b200_obs *o, int64_t cutoff);
+int smcpp_b200_obs_break_long_spans(smcpp_b200_obs *o, int64_t span_cutoff, int64_t *n_pieces);
+int smcpp_b200_obs_piece_offsets(smcpp_b200_obs *o, int64_t *offsets /* n_pieces + 1 */);
+int smcpp_b200_obs_select_piece(smcpp_b200_obs *o, int64_t piece, int64_t row_begin, int64_t row_end);
 int64_t smcpp_b200_obs_rows(const smcpp_b200_obs *o);
 float smcpp_b200_obs_last_ms(const smcpp_b200_obs *o);
 int smcpp_b200_obs_download(smcpp_b200_obs *o, int32_t *rows /* rows() x (1 + 3 npop) */);

@@ -138,3 +138,54 @@ long smcb_oracle_compress(const int32_t *data, long K, int W, int32_t *out)
     }
     return r;
 }
+
+/* recode_nonseg(contig, cutoff) with a cutoff given: reference smcpp/estimation_tools.py:88-114 (in place).  Runs of
+ * homozygosity longer than `cutoff` -- span > cutoff, every a == 0 and every b == 0 -- become missing (a = -1, nb = 0).
+ * Returns the number of rows changed.  (cutoff = None only warns in the reference and changes nothing.) */
+long smcb_oracle_recode_nonseg(int32_t *data, long K, int npop, long cutoff)
+{
+    const int W = 1 + 3 * npop;
+    long changed = 0;
+    for (long j = 0; j < K; ++j) {
+        int run = data[j * W] > cutoff;
+        for (int n = 0; n < npop; ++n)
+            if (data[j * W + 1 + 3 * n] != 0 || data[j * W + 2 + 3 * n] != 0) run = 0;
+        if (run) {
+            for (int n = 0; n < npop; ++n) { data[j * W + 1 + 3 * n] = -1; data[j * W + 3 + 3 * n] = 0; }
+            ++changed;
+        }
+    }
+    return changed;
+}
+
+/* break_long_spans(contig, span_cutoff): reference smcpp/estimation_tools.py:117-167.  The contig is cut at every long
+ * missing row (span >= cutoff, every a == -1, every nb == 0); the long rows are dropped and every piece gets a one-base
+ * missing row in front (:129-131, :143).  Output: the pieces one after the other in `out` (K + 1 rows: every long row's
+ * place is taken by the next piece's leading row) and piece_off[0..n_pieces] (row offsets into out).  Returns n_pieces. */
+long smcb_oracle_break_long_spans(const int32_t *data, long K, int npop, long cutoff, int32_t *out, long *piece_off)
+{
+    const int W = 1 + 3 * npop;
+    int32_t miss[7];
+    memset(miss, 0, sizeof miss);
+    miss[0] = 1;
+    for (int n = 0; n < npop; ++n) miss[1 + 3 * n] = -1;
+    long r = 0, pieces = 0;
+    piece_off[pieces++] = 0;
+    memcpy(out + r * W, miss, W * sizeof(int32_t));
+    ++r;
+    for (long j = 0; j < K; ++j) {
+        const int32_t *row = data + j * W;
+        int lng = row[0] >= cutoff;
+        for (int n = 0; n < npop; ++n)
+            if (row[1 + 3 * n] != -1 || row[3 + 3 * n] != 0) lng = 0;
+        if (lng) {
+            piece_off[pieces++] = r;
+            memcpy(out + r * W, miss, W * sizeof(int32_t));
+        } else {
+            memcpy(out + r * W, row, W * sizeof(int32_t));
+        }
+        ++r;
+    }
+    piece_off[pieces] = r;
+    return pieces;
+}

@@ -26,7 +26,7 @@ def lib():
     global _LIB
     if _LIB is None:
         _LIB = ctypes.CDLL(build())
-        for f in ("smcb_oracle_thin", "smcb_oracle_bin", "smcb_oracle_compress"):
+        for f in ("smcb_oracle_thin", "smcb_oracle_bin", "smcb_oracle_compress", "smcb_oracle_recode_nonseg", "smcb_oracle_break_long_spans"):
             getattr(_LIB, f).restype = ctypes.c_long
         _LIB.smcb_oracle_recode_monomorphic.restype = None
     return _LIB
@@ -72,3 +72,20 @@ def compress_repeated_obs(data) -> np.ndarray:
     r = lib().smcb_oracle_compress(data.ctypes.data_as(I32P), ctypes.c_long(data.shape[0]), ctypes.c_int(data.shape[1]),
                                    out.ctypes.data_as(I32P))
     return out[:r].copy()
+
+
+def recode_nonseg(data, cutoff: int) -> np.ndarray:
+    data, npop = _rows(data)
+    data = data.copy()
+    lib().smcb_oracle_recode_nonseg(data.ctypes.data_as(I32P), ctypes.c_long(data.shape[0]), ctypes.c_int(npop), ctypes.c_long(cutoff))
+    return data
+
+
+def break_long_spans(data, cutoff: int) -> list:
+    """List of pieces (each with its leading missing row), as the reference returns one Contig per piece."""
+    data, npop = _rows(data)
+    out = np.zeros((data.shape[0] + 1, data.shape[1]), np.int32)
+    off = np.zeros(data.shape[0] + 2, np.int64)
+    n = lib().smcb_oracle_break_long_spans(data.ctypes.data_as(I32P), ctypes.c_long(data.shape[0]), ctypes.c_int(npop), ctypes.c_long(cutoff),
+                                           out.ctypes.data_as(I32P), off.ctypes.data_as(LP))
+    return [out[off[i]:off[i + 1]].copy() for i in range(n)]

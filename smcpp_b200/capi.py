@@ -47,7 +47,8 @@ SYMBOLS = [
     "smcpp_b200_fetch_gamma",
     "smcpp_b200_obs_create", "smcpp_b200_obs_destroy", "smcpp_b200_obs_last_error", "smcpp_b200_obs_upload", "smcpp_b200_obs_thin",
     "smcpp_b200_obs_bin", "smcpp_b200_obs_recode_monomorphic", "smcpp_b200_obs_compress", "smcpp_b200_obs_rows", "smcpp_b200_obs_last_ms",
-    "smcpp_b200_obs_download",
+    "smcpp_b200_obs_download", "smcpp_b200_obs_recode_nonseg", "smcpp_b200_obs_break_long_spans", "smcpp_b200_obs_piece_offsets",
+    "smcpp_b200_obs_select_piece",
 ]
 
 
@@ -369,6 +370,25 @@ class ObsPipeline:
     def compress(self):
         self._check(lib().smcpp_b200_obs_compress(self._h), "compress")
         return self._done("compress")
+
+    def recode_nonseg(self, cutoff: int):
+        self._check(lib().smcpp_b200_obs_recode_nonseg(self._h, ctypes.c_int64(cutoff)), "recode_nonseg")
+        return self._done("recode_nonseg")
+
+    def break_long_spans(self, span_cutoff: int) -> np.ndarray:
+        """Cuts the current rows at long missing spans; returns the piece offsets (n_pieces + 1) into the broken array, which
+        stays on the device; select_piece(p) makes one piece the current rows."""
+        npieces = ctypes.c_int64()
+        self._check(lib().smcpp_b200_obs_break_long_spans(self._h, ctypes.c_int64(span_cutoff), ctypes.byref(npieces)), "break_long_spans")
+        self._done("break_long_spans")
+        self.piece_offsets = np.empty(npieces.value + 1, np.int64)
+        self._check(lib().smcpp_b200_obs_piece_offsets(self._h, self.piece_offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "piece_offsets")
+        return self.piece_offsets
+
+    def select_piece(self, p: int):
+        self._check(lib().smcpp_b200_obs_select_piece(self._h, ctypes.c_int64(p), ctypes.c_int64(int(self.piece_offsets[p])),
+                                                      ctypes.c_int64(int(self.piece_offsets[p + 1]))), "select_piece")
+        return self
 
     @property
     def n_rows(self) -> int:

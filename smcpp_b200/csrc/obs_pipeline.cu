@@ -264,6 +264,49 @@ __global__ void k_compress_write(const int32_t *rows, const int64_t *pos, const 
     }
 }
 
+// ---- recode_nonseg / break_long_spans ---------------------------------------------------------------------------
+__global__ void k_recode_nonseg(int32_t *rows, int64_t n, Params P, int64_t cutoff)
+{
+    const int W = P.W;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        Row r = load_row(rows, j, W);
+        bool run = r.v[0] > cutoff;
+        for (int p = 0; p < P.npop; ++p) run = run && r.v[1 + 3 * p] == 0 && r.v[2 + 3 * p] == 0;
+        if (run) {
+            for (int p = 0; p < P.npop; ++p) { r.v[1 + 3 * p] = -1; r.v[3 + 3 * p] = 0; }
+            store_row(rows, j, W, r);
+        }
+    }
+}
+// Every long missing row is dropped and every piece gets a one-base missing row in front, so row j simply moves to
+// j + 1 and a long row's place is taken by the next piece's leading row: no compaction, only the piece offsets need a scan.
+__global__ void k_break_long_spans(const int32_t *rows, int64_t n, Params P, int64_t cutoff, int32_t *out, int64_t *flag)
+{
+    const int W = P.W;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j <= n; j += (int64_t)gridDim.x * blockDim.x) {
+        Row r;
+        bool lng = j == 0;                       // slot 0: the first piece's leading row
+        if (j > 0) {
+            r = load_row(rows, j - 1, W);
+            lng = r.v[0] >= cutoff;
+            for (int p = 0; p < P.npop; ++p) lng = lng && r.v[1 + 3 * p] == -1 && r.v[3 + 3 * p] == 0;
+        }
+        if (lng) {
+            for (int c = 0; c < W; ++c) r.v[c] = 0;
+            r.v[0] = 1;
+            for (int p = 0; p < P.npop; ++p) r.v[1 + 3 * p] = -1;
+        }
+        store_row(out, j, W, r);
+        flag[j] = lng;
+    }
+}
+__global__ void k_piece_offsets(const int64_t *flag_scan, const int64_t *flag, int64_t n1, int64_t n_pieces, int64_t *off)
+{
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n1; j += (int64_t)gridDim.x * blockDim.x)
+        if (flag[j]) off[flag_scan[j]] = j;
+    if (blockIdx.x == 0 && threadIdx.x == 0) off[n_pieces] = n1;
+}
+
 int grid_for(int64_t n)
 {
     int64_t b = (n + 255) / 256;
@@ -281,6 +324,9 @@ struct smcpp_b200_obs {
     int npop = 0, W = 0;
     int64_t n = 0;                     // rows currently held
     Buf<int32_t> rows, rows2;          // current rows / output of the running step (swapped)
+    Buf<int32_t> pieces;               // result of break_long_spans (all pieces, one after the other)
+    Buf<int64_t> piece_off;            // [n_pieces + 1] row offsets into `pieces`
+    int64_t n_pieces = 0, n_piece_rows = 0;
     Buf<int64_t> a64, b64, c64, part;  // spans / counts / flags, their scans, run starts; chunk partition
     Buf<unsigned char> cub_tmp;
     int64_t *h_pin = nullptr;          // 2 pinned int64 for scalar read-backs
@@ -371,7 +417,7 @@ void smcpp_b200_obs_destroy(smcpp_b200_obs *o)
     if (!o) return;
     cudaSetDevice(o->device);
     cudaStreamSynchronize(o->st);
-    o->rows.release(); o->rows2.release(); o->a64.release(); o->b64.release(); o->c64.release(); o->part.release(); o->cub_tmp.release();
+    o->rows.release(); o->rows2.release(); o->pieces.release(); o->piece_off.release(); o->a64.release(); o->b64.release(); o->c64.release(); o->part.release(); o->cub_tmp.release();
     if (o->h_pin) cudaFreeHost(o->h_pin);
     if (o->e0) cudaEventDestroy(o->e0);
     if (o->e1) cudaEventDestroy(o->e1);
@@ -473,6 +519,69 @@ int smcpp_b200_obs_recode_monomorphic(smcpp_b200_obs *o, const int64_t *a)
     OCU(cudaStreamSynchronize(o->st));
     OCU(cudaGetLastError());
     cudaEventElapsedTime(&o->last_ms, o->e0, o->e1);
+    return 0;
+}
+
+int smcpp_b200_obs_recode_nonseg(smcpp_b200_obs *o, int64_t cutoff)
+{
+    if (!o || o->n <= 0) return 1;
+    if (cutoff < 0) { o->err = "obs_recode_nonseg: cutoff >= 0 required"; return 1; }
+    OCU(cudaSetDevice(o->device));
+    cudaEventRecord(o->e0, o->st);
+    k_recode_nonseg<<<grid_for(o->n), 256, 0, o->st>>>(o->rows.p, o->n, make_params(o, nullptr), cutoff);
+    cudaEventRecord(o->e1, o->st);
+    OCU(cudaStreamSynchronize(o->st));
+    OCU(cudaGetLastError());
+    cudaEventElapsedTime(&o->last_ms, o->e0, o->e1);
+    return 0;
+}
+
+int smcpp_b200_obs_break_long_spans(smcpp_b200_obs *o, int64_t span_cutoff, int64_t *n_pieces)
+{
+    if (!o || o->n <= 0 || !n_pieces) return 1;
+    OCU(cudaSetDevice(o->device));
+    const int64_t n1 = o->n + 1;
+    OCU(o->pieces.ensure((size_t)n1 * o->W));
+    OCU(o->a64.ensure(n1));
+    OCU(o->c64.ensure(n1));
+    cudaEventRecord(o->e0, o->st);
+    k_break_long_spans<<<grid_for(n1), 256, 0, o->st>>>(o->rows.p, o->n, make_params(o, nullptr), span_cutoff, o->pieces.p, o->a64.p);
+    int64_t np = 0;
+    if (scan_total(o, o->a64.p, o->c64.p, n1, &np)) return 1;
+    OCU(o->piece_off.ensure(np + 1));
+    k_piece_offsets<<<grid_for(n1), 256, 0, o->st>>>(o->c64.p, o->a64.p, n1, np, o->piece_off.p);
+    cudaEventRecord(o->e1, o->st);
+    OCU(cudaStreamSynchronize(o->st));
+    OCU(cudaGetLastError());
+    cudaEventElapsedTime(&o->last_ms, o->e0, o->e1);
+    o->n_pieces = np;
+    o->n_piece_rows = n1;
+    *n_pieces = np;
+    return 0;
+}
+
+int smcpp_b200_obs_piece_offsets(smcpp_b200_obs *o, int64_t *offsets)
+{
+    if (!o || !offsets || o->n_pieces <= 0) { if (o) o->err = "obs_piece_offsets: break_long_spans has not been run"; return 1; }
+    OCU(cudaSetDevice(o->device));
+    OCU(cudaMemcpyAsync(offsets, o->piece_off.p, (size_t)(o->n_pieces + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, o->st));
+    OCU(cudaStreamSynchronize(o->st));
+    return 0;
+}
+
+int smcpp_b200_obs_select_piece(smcpp_b200_obs *o, int64_t piece, int64_t row_begin, int64_t row_end)
+{
+    if (!o || o->n_pieces <= 0) { if (o) o->err = "obs_select_piece: break_long_spans has not been run"; return 1; }
+    if (piece < 0 || piece >= o->n_pieces || row_begin < 0 || row_end > o->n_piece_rows || row_begin >= row_end) {
+        o->err = "obs_select_piece: piece / row range out of bounds";
+        return 1;
+    }
+    OCU(cudaSetDevice(o->device));
+    const int64_t n = row_end - row_begin;
+    OCU(o->rows.ensure((size_t)n * o->W));
+    OCU(cudaMemcpyAsync(o->rows.p, o->pieces.p + (size_t)row_begin * o->W, (size_t)n * o->W * sizeof(int32_t), cudaMemcpyDeviceToDevice, o->st));
+    OCU(cudaStreamSynchronize(o->st));
+    o->n = n;
     return 0;
 }
 

@@ -98,6 +98,14 @@ def main():
     et = build_reference_cython()
     compress = reference_function(os.path.join(REF, "estimation_tools.py"), "compress_repeated_obs")
     recode = reference_function(os.path.join(REF, "data_filter.py"), "_recode", cls="RecodeMonomorphic")
+    recode_nonseg = reference_function(os.path.join(REF, "estimation_tools.py"), "recode_nonseg")
+    break_long_spans = reference_function(os.path.join(REF, "estimation_tools.py"), "break_long_spans")
+    contig_mod = {}
+    exec(compile(open(os.path.join(REF, "contig.py")).read(), os.path.join(REF, "contig.py"), "exec"), contig_mod)
+    import logging
+    for f in (recode_nonseg, break_long_spans):     # module globals the two functions use
+        f.__globals__["Contig"] = contig_mod["Contig"]
+        f.__globals__["logger"] = logging.getLogger("ref")
     out = {}
     cases = [("p1", 1, (8,), (2,), 4000, 37, 100, True), ("p1_dense", 1, (5,), (2,), 3000, 7, 10, False),
              ("p1_w1000", 1, (20,), (2,), 5000, 1521, 1000, True), ("p2_20", 2, (6, 4), (2, 0), 3000, 53, 100, True),
@@ -110,6 +118,16 @@ def main():
                           [10, 0, 0, 0]], np.int32)
         else:
             d = raw_rows(rng, L, npop, n, a, long_runs)
+        # base.py:50-52 front of the chain on the raw rows: RecodeNonseg(cutoff) -> Compress -> BreakLongSpans(cutoff)
+        cut_ns, cut_bl = (400, 300) if long_runs else (4, 3)
+        c0 = contig_mod["Contig"](pid=("p",) * npop, data=d.copy(), n=n, a=a, fn="golden")
+        recode_nonseg(c0, cut_ns)
+        out[f"{name}__nonseg"] = c0.data.copy()
+        c0.data = compress(c0.data)
+        pieces = break_long_spans(c0, cut_bl)
+        out[f"{name}__pieces"] = np.concatenate([p.data for p in pieces], axis=0)
+        out[f"{name}__piece_len"] = np.array([p.data.shape[0] for p in pieces], np.int64)
+        out[f"{name}__cutoffs"] = np.array([cut_ns, cut_bl], np.int64)
         thin = et.thin_data(d.copy(), thinning)
         c = FakeContig(thin.copy(), a)
         binned = np.array(et.bin_observations(c, w))

@@ -34,6 +34,18 @@ def test_oracle_matches_reference_outputs(name):
     assert np.array_equal(obsport.compress_repeated_obs(g["raw"]), g["raw_compressed"])
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_front_of_chain_matches_reference(name):
+    # RecodeNonseg(cutoff) -> Compress -> BreakLongSpans(cutoff): reference smcpp/analysis/base.py:50-52
+    g, npop, thinning, w = case(name)
+    cut_ns, cut_bl = (int(x) for x in g["cutoffs"])
+    ns = obsport.recode_nonseg(g["raw"], cut_ns)
+    assert np.array_equal(ns, g["nonseg"])
+    pieces = obsport.break_long_spans(obsport.compress_repeated_obs(ns), cut_bl)
+    assert [p.shape[0] for p in pieces] == list(g["piece_len"])
+    assert np.array_equal(np.concatenate(pieces, axis=0), g["pieces"])
+
+
 def test_oracle_invariants():
     g, npop, thinning, w = case("p1")
     thin = obsport.thin_data(g["raw"], thinning)
@@ -97,6 +109,25 @@ def test_gpu_pipeline_against_oracle_on_fresh_inputs(npop, n, a, L, thinning, w,
     rec = obsport.recode_monomorphic(binned, a)
     assert np.array_equal(p.recode_monomorphic(a).rows(), rec)
     assert np.array_equal(p.compress().rows(), obsport.compress_repeated_obs(rec))
+    p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_front_of_chain_matches_reference(name):
+    from smcpp_b200 import capi
+    g, npop, thinning, w = case(name)
+    cut_ns, cut_bl = (int(x) for x in g["cutoffs"])
+    p = capi.ObsPipeline(g["raw"])
+    assert np.array_equal(p.recode_nonseg(cut_ns).rows(), g["nonseg"])
+    off = p.compress().break_long_spans(cut_bl)
+    assert list(np.diff(off)) == list(g["piece_len"])
+    got = [p.select_piece(i).rows() for i in range(len(off) - 1)]
+    assert np.array_equal(np.concatenate(got, axis=0), g["pieces"])
+    # a piece goes on through the rest of the chain like any contig
+    big = int(np.argmax(np.diff(off)))
+    want = obsport.compress_repeated_obs(obsport.bin_observations(obsport.thin_data(got[big], thinning), g["a"], w))
+    assert np.array_equal(p.select_piece(big).thin(thinning).bin(g["a"], w).compress().rows(), want)
     p.close()
 
 
