@@ -102,9 +102,9 @@ struct Work {
     float *alpha;            // [n_cols][Mp]  chunk-local alpha_hat columns (column 0 of a chunk = its start)
     float *cnorm;            // [total]       float forward normaliser of span-1 blocks (hmm.cpp:87)
     double *bvec;            // [total][Mp]   beta_l (span 1) or w_l = P_r^T beta_l (span > 1)
-    double *uvec;            // [total][32]   M <= 32: u_l = Pinv_r alpha_hat_{l-1} of span>1 blocks, written by the forward pass
-    double *Ritem;           // [n_items][32*32]  per-item partials of R_e (M <= 32)
-    double *ditem;           // [n_items][32]     per-item partials of D_e
+    double *uvec;            // [total][Mp]   M <= 64: u_l = Pinv_r alpha_hat_{l-1} of span>1 blocks, written by the forward pass
+    double *Ritem;           // [n_items][Mp*Mp]  per-item partials of R_e (M <= 64)
+    double *ditem;           // [n_items][Mp]     per-item partials of D_e
     float *start_used;       // [n_chunks][Mp]
     float *end_alpha;        // [n_chunks][Mp]
     float *end_alpha_prev;   // [n_chunks][Mp] snapshot of the previous sweep
@@ -139,6 +139,7 @@ void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, c
 size_t sums_stride(const Model &m);
 int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
+void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 64
 constexpr int kItemBlocks = 4096;   // span>1 blocks per work item of k_stats32e
 void launch_setup_pwtab(const Model &m, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32

@@ -68,7 +68,7 @@ def one_case(rng, idx):
     if rng.random() < 0.15:
         opts = {"force_sequential": 1}
     desc = {"case": idx, "npop": npop, "M": M, "C": C, "L": [c.shape[0] for c in contigs], "K": K, "n_eig": len(eig_idx), "spans": span_mode, "opts": opts}
-    if eig["eig_cplx"].any():
+    if eig["eig_cplx"].any() or len(eig_idx) > 30:     # documented limit: at most 30 distinct keys with span > 1 (kcode has 5 bits for them)
         return None, desc
     ctx = capi.Context(0)
     try:
@@ -115,7 +115,7 @@ def main():
         if not (worst <= 1.0):
             bad += 1
             print("FAIL", json.dumps(desc), "worst error / tolerance = %.3g" % worst, flush=True)
-    print(f"fuzz: {ncases} cases, {bad} failed, {skipped} skipped (complex spectrum), worst error/tolerance {worst_all:.3g}")
+    print(f"fuzz: {ncases} cases, {bad} failed, {skipped} skipped (complex spectrum / > 30 eigen keys), worst error/tolerance {worst_all:.3g}")
     return 1 if bad else 0
 
 
