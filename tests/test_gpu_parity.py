@@ -406,3 +406,40 @@ def test_randomised_parity_sweep():
             assert w <= 1.0, desc
             worst = max(worst, w)
     assert worst > 0.0
+
+
+def test_plain_c_consumer_agrees_with_the_python_binding(tmp_path):
+    """examples/cabi_estep.c run as a program: same toy inputs through ctypes must give the same numbers."""
+    import math
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "cabi_estep"
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "cabi_estep.c"),
+                           "-L" + os.path.join(root, "smcpp_b200"), "-lsmcpp_b200", "-Wl,-rpath," + os.path.join(root, "smcpp_b200"), "-lm",
+                           "-o", str(exe)])
+    txt = subprocess.check_output([str(exe)], text=True)
+    ll_c = [float(x) for x in txt.splitlines()[1].split()[1:3]]
+    M = 4
+    c0 = np.zeros((41, 4), np.int32)
+    for i in range(41):
+        c0[i] = [3 + 7 * (i % 5), -1 if i == 20 else 0, 0, 0] if i % 2 == 0 else [1, 1 + (i % 3 == 0), 2 if i % 7 == 1 else 0, 3 if i % 7 == 1 else 0]
+    c1 = np.zeros((23, 4), np.int32)
+    for i in range(23):
+        c1[i] = [2 + 11 * (i % 3), 0, 0, 0] if i % 2 == 0 else [1, 1, 0, 0]
+    ctx = capi.Context(0)
+    ctx.set_contigs([c0, c1], 1)
+    keys = ctx.keys
+    pi = np.arange(1, M + 1) / (M * (M + 1) / 2.0)
+    T = np.array([[50.0 if i == j else 1.0 / (1.0 + abs(i - j)) for j in range(M)] for i in range(M)])
+    T /= T.sum(1, keepdims=True)
+    E = np.array([[1.0 if a < 0 else math.exp(-0.02 * (i + 1)) if (a == 0 and b == 0) else 0.01 * (i + 1) * (1 + a) / (1.0 + b)
+                   for i in range(M)] for a, b, nb in keys])
+    out = ctx.estep(pi, T, E, None)
+    assert np.allclose(out["ll"], ll_c, rtol=1e-11, atol=0)
+    # and both agree with the port
+    eig = ctx.eigensystems(T, E)
+    ref = {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
+    for c, obs in enumerate((c0, c1)):
+        assert abs(port.hmm_estep(obs, ref)["ll"] - ll_c[c]) <= LL_RTOL * abs(ll_c[c])
+    ctx.close()

@@ -46,3 +46,14 @@ def test_built_for_sm100a():
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_header_is_valid_c99_and_a_plain_c_consumer_links(tmp_path):
+    """examples/cabi_estep.c: strict C99 against include/smcpp_b200.h, linked to the in-tree library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "cabi_estep"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "cabi_estep.c"), "-L" + os.path.join(root, "smcpp_b200"), "-lsmcpp_b200",
+                           "-Wl,-rpath," + os.path.join(root, "smcpp_b200"), "-lm", "-o", str(exe)])
+    assert exe.exists()
