@@ -623,7 +623,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     std::vector<int2> erec;
     std::vector<int64_t> it_start;
     std::vector<int32_t> it_len, it_contig, it_eig, it_off;
-    if ((Mp == 32 || Mp == 64) && NEp > 0) {
+    if ((Mp == 32 || Mp == 64 || Mp == 128) && NEp > 0) {
         const int NS = (int)ctx->span_list.size();
         // item size: up to kItemBlocks, but small inputs still get ~4 items per SM (about half of the blocks have span > 1)
         const int64_t item_blocks =
@@ -725,7 +725,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->w_alpha.ensure((size_t)cols * Mp));
     CU(ctx->w_cnorm.ensure(ctx->total));
     CU(ctx->w_bvec.ensure((size_t)ctx->total * Mp));
-    if (Mp == 32 || Mp == 64) {
+    if (Mp == 32 || Mp == 64 || Mp == 128) {
         CU(ctx->w_uvec.ensure((size_t)ctx->total * Mp));
         CU(ctx->w_Ritem.ensure((size_t)std::max(1, ctx->n_items) * Mp * Mp));
         CU(ctx->w_ditem.ensure((size_t)std::max(1, ctx->n_items) * Mp));
@@ -901,7 +901,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     launch_finalize(m, p, w, ctx->st);
     cudaEventRecord(ctx->ev[4], ctx->st);
     // statistics: k_stats32 (+ k_stats32e when there are span>1 items) or the generic k_stats; finalize: 3 kernels
-    ctx->stats.kernel_launches += (((m.Mp == 32 || m.Mp == 64) && p.n_items > 0) ? 2 : 1) + 3;
+    ctx->stats.kernel_launches += (((m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0) ? 2 : 1) + 3;
     CU(cudaGetLastError());
     ctx->stats.n_chunks = p.n_chunks;
     ctx->stats.chunk_blocks = p.chunk_blocks;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
 #pragma unroll
                 for (int r = 0; r < R; ++r) u[r] = fma(__ldg(PinvT + (size_t)i * Mp + lane + 32 * r), xi, u[r]);
             }
-            if (Mp == 64 && b >= s) {   // operand of the M <= 64 statistics kernels (stats32.cu: k_stats64e)
+            if ((Mp == 64 || Mp == 128) && b >= s) {   // operand of the tiled statistics kernels (stats32.cu: k_statsTe); Mp = 96 stays generic
 #pragma unroll
                 for (int r = 0; r < R; ++r) w.uvec[(size_t)(g0 + b) * Mp + lane + 32 * r] = u[r];
             }
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
     if (m.Mp == 32) { launch_stats32(m, p, w, st); return; }
-    if (m.Mp == 64) { launch_stats64(m, p, w, st); return; }
+    if (m.Mp == 64 || m.Mp == 128) { launch_stats64(m, p, w, st); return; }
     const int smem = stats_smem_bytes(m);
     // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
     static int configured[5] = {0, 0, 0, 0, 0};
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w
     else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 2u << (int)(y / Mp); }
     else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 1u; }
     double acc = 0.0;
-    if ((Mp == 32 || Mp == 64) && x >= oR && x < oG) {
+    if ((Mp == 32 || Mp == 64 || Mp == 128) && x >= oR && x < oG) {
         // M <= 64: R_e / D_e partials come per work item of k_stats32e / k_stats64e (fixed order: bitwise reproducible)
         const bool isR = x < oD;
         const size_t y = isR ? x - oR : x - oD;

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             if (e == hot) gemv_hot<NS, FRAG>(rF_Pinv, sF_Pinv, m.F_Pinv + (size_t)e * MM, xd, u, lane);
             else gemv8<NS, false>(m.F_Pinv + (size_t)e * MM, xd, u, lane);
             const int sp = adv ? span : 1;
-            if constexpr (NS <= 2) {
+            {
                 // u_l = Pinv_r alpha_hat_{l-1} is an operand of the statistics pass (stats32.cu), stored in eigen-index order
                 if (adv && cur >= s) {
                     double *ud = w.uvec + (size_t)(g0 + cur) * MP + 2 * q;

@@ -404,16 +404,30 @@ __global__ void __launch_bounds__(kSEWarps * 32, 2) k_stats32e(Model m, Plan p, 
 }
 
 // =====================================================================================================================
-// M in (32, 64]: the same two kernels with ONE WARP PER 32x32 TILE of the 64x64 accumulators (CTA = 4 warps = tiles
-// (ta, tb)).  Every warp walks all groups of its slab / item: it reads the full 64-long vectors for the per-block scalars
-// (p = alpha . beta, resp. C) and feeds the tensor pipe with the ta-half of the row operand and the tb-half of the column
-// operand; the redundant loads of the four warps hit L1.  Vector-shaped results (gamma sums, D_e) come from the tb = 0 warps.
+// M in (32, 128] (NS = Mp / 32 in {2, 4}): the same two kernels with ONE WARP PER 32x32 TILE of the Mp x Mp accumulators.
+// A CTA has 4 warps; warp w takes the tiles (ta, tb) = (t / NS, t % NS), t = w, w + 4, ... -- one tile per warp at NS = 2,
+// four in sequence at NS = 4 -- and walks ALL groups of its slab / item for each: it reads the full Mp-long vectors for
+// the per-block scalars (p = alpha . beta, resp. C) and feeds the tensor pipe with the ta-part of the row operand and the
+// tb-part of the column operand; the redundant loads of the four warps hit L1 / L2.  Vector-shaped results (gamma sums,
+// D_e) come from the tb = 0 tiles.
 // =====================================================================================================================
-constexpr int kS64Warps = 4;
-constexpr int kS64MaxKeysSmem = 128;
+constexpr int kSTWarps = 4;
+constexpr int kSTMaxGsBytes = 64 * 1024;       // per-key gamma sums in shared memory up to this size, else in global memory
 
-__global__ void __launch_bounds__(kS64Warps * 32, 2) k_stats64(Model m, Plan p, Work w, int gs_in_smem)
+template <int NS, typename V>
+__device__ __forceinline__ V pick(const V (&a)[NS], int i)      // a[i] without dynamic register indexing
 {
+    V r = a[0];
+#pragma unroll
+    for (int x = 1; x < NS; ++x)
+        if (x == i) r = a[x];
+    return r;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kSTWarps * 32, 2) k_statsT(Model m, Plan p, Work w, int gs_in_smem)
+{
+    constexpr int MP = 32 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = m.K, NE = m.n_eig;
     const int slab = blockIdx.x;
@@ -423,122 +437,134 @@ __global__ void __launch_bounds__(kS64Warps * 32, 2) k_stats64(Model m, Plan p, 
     const int64_t g0 = p.blk_off[t];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
-    const int ta = warp >> 1, tb = warp & 1;
     const int2 *rec = p.srec + g0 + s0;
     const int32_t *seg = p.seg + (size_t)slab * (NE + 2);
     double *tiles = reinterpret_cast<double *>(smem_raw);                   // [4][32*33]
-    double *gs_s = tiles + (size_t)kS64Warps * 32 * 33;                     // [K][64] when gs_in_smem
-    double *gs = gs_in_smem ? gs_s : w.gspart + (size_t)slab * K * 64;
+    double *gs_s = tiles + (size_t)kSTWarps * 32 * 33;                      // [K][MP] when gs_in_smem
+    double *gs = gs_in_smem ? gs_s : w.gspart + (size_t)slab * K * MP;
     const int Lc = p.chunk_blocks;
     const int64_t colbase = p.col_off[t];
     auto alpha_col = [&](int b) -> const float * {
         const int cb = b / Lc;
-        return w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (b - cb * Lc)) * 64;
+        return w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (b - cb * Lc)) * MP;
     };
-    for (int x = tid; x < K * 64; x += kS64Warps * 32) gs[x] = 0.0;
+    for (int x = tid; x < K * MP; x += kSTWarps * 32) gs[x] = 0.0;
     __syncthreads();
     const int d0 = seg[0], d1 = seg[1];
     const int ngrp = (d1 - d0 + 3) >> 2;
-    double acc[4][4][2];
+    double *tile = tiles + (size_t)warp * 32 * 33;
+    double *Xp = w.Xpart + (size_t)slab * MP * MP;
+
+    for (int tix = warp; tix < NS * NS; tix += kSTWarps) {
+        const int ta = tix / NS, tb = tix % NS;
+        double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    double gacc[4] = {0.0, 0.0, 0.0, 0.0};
-    int cur = -1;
-    auto flush = [&](int key) {          // tb == 0 warps only: this warp is the only writer of (key, its 32 states)
-        if (key < 0) return;
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        double gacc[4] = {0.0, 0.0, 0.0, 0.0};
+        int cur = -1;
+        auto flush = [&](int key) {          // tb == 0 tiles only: the only writer of (key, these 32 states)
+            if (key < 0) return;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const double v = sum_over_q(gacc[nt]);
-            if (q == 0) gs[(size_t)key * 64 + 32 * ta + 4 * r + nt] += v;
-            gacc[nt] = 0.0;
-        }
-    };
-    struct Ops { float4 a4, cA, cB; dbl4 bA, bB, e4; float cn; int k; };
-    auto load_rec = [&](int g) { return (g < ngrp && d0 + 4 * g + q < d1) ? __ldg(rec + d0 + 4 * g + q) : make_int2(0, -1); };
-    auto load_ops = [&](int2 rc) {
-        Ops o;
-        o.k = rc.y;
-        const int64_t gb = g0 + rc.x;
-        const float4 *ap = reinterpret_cast<const float4 *>(alpha_col(rc.x));
-        o.a4 = __ldg(ap + 8 * ta + r);
-        o.cA = __ldg(ap + 16 + r);
-        o.cB = __ldg(ap + 24 + r);
-        const double *bv = w.bvec + (size_t)gb * 64;
-        o.bA = ld4d(bv + 4 * r);
-        o.bB = ld4d(bv + 32 + 4 * r);
-        o.e4 = ld4d(m.E + (size_t)(rc.y < 0 ? 0 : rc.y) * 64 + 32 * tb + 4 * r);
-        o.cn = __ldg(w.cnorm + gb);
-        return o;
-    };
-    auto process = [&](const Ops &o) {
-        const bool valid = o.k >= 0;
-        const double cA[4] = {o.cA.x, o.cA.y, o.cA.z, o.cA.w}, cB[4] = {o.cB.x, o.cB.y, o.cB.z, o.cB.w};
-        const double av[4] = {valid ? o.a4.x : 0.0, valid ? o.a4.y : 0.0, valid ? o.a4.z : 0.0, valid ? o.a4.w : 0.0};
-        double pp = 0.0;
+            for (int nt = 0; nt < 4; ++nt) {
+                const double v = sum_over_q(gacc[nt]);
+                if (q == 0) gs[(size_t)key * MP + 32 * ta + 4 * r + nt] += v;
+                gacc[nt] = 0.0;
+            }
+        };
+        struct Ops { float4 a4; float4 c[NS]; dbl4 b[NS]; dbl4 e4; float cn; int k; };
+        auto load_rec = [&](int g) { return (g < ngrp && d0 + 4 * g + q < d1) ? __ldg(rec + d0 + 4 * g + q) : make_int2(0, -1); };
+        auto load_ops = [&](int2 rc) {
+            Ops o;
+            o.k = rc.y;
+            const int64_t gb = g0 + rc.x;
+            const float4 *ap = reinterpret_cast<const float4 *>(alpha_col(rc.x));
+            o.a4 = __ldg(ap + 8 * ta + r);
+            const double *bv = w.bvec + (size_t)gb * MP;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pp = fma(cA[i], o.bA.v[i], fma(cB[i], o.bB.v[i], pp));
-        pp = sum_over_r(valid ? pp : 0.0);
-        const double inv_cp = valid ? 1.0 / (pp * (double)o.cn) : 0.0;
-        const double inv_p = inv_cp * (double)o.cn;
-        double bvv[4];
+            for (int x = 0; x < NS; ++x) {
+                o.c[x] = __ldg(ap + MP / 4 + 8 * x + r);
+                o.b[x] = ld4d(bv + 32 * x + 4 * r);
+            }
+            o.e4 = ld4d(m.E + (size_t)(rc.y < 0 ? 0 : rc.y) * MP + 32 * tb + 4 * r);
+            o.cn = __ldg(w.cnorm + gb);
+            return o;
+        };
+        auto process = [&](const Ops &o) {
+            const bool valid = o.k >= 0;
+            double pp = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bvv[i] = (tb ? o.bB.v[i] : o.bA.v[i]) * o.e4.v[i] * inv_cp;
+            for (int x = 0; x < NS; ++x) {
+                pp = fma((double)o.c[x].x, o.b[x].v[0], pp);
+                pp = fma((double)o.c[x].y, o.b[x].v[1], pp);
+                pp = fma((double)o.c[x].z, o.b[x].v[2], pp);
+                pp = fma((double)o.c[x].w, o.b[x].v[3], pp);
+            }
+            pp = sum_over_r(valid ? pp : 0.0);
+            const double inv_cp = valid ? 1.0 / (pp * (double)o.cn) : 0.0;
+            const double inv_p = inv_cp * (double)o.cn;
+            const double av[4] = {valid ? o.a4.x : 0.0, valid ? o.a4.y : 0.0, valid ? o.a4.z : 0.0, valid ? o.a4.w : 0.0};
+            const dbl4 btb = pick<NS>(o.b, tb);
+            double bvv[4];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+            for (int i = 0; i < 4; ++i) bvv[i] = btb.v[i] * o.e4.v[i] * inv_cp;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bvv[nt]);
-        if (tb == 0) {
-            double vv[4];
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) vv[i] = (ta ? cB[i] * o.bB.v[i] : cA[i] * o.bA.v[i]) * inv_p;
-            const int k = o.k;
-            const int k0 = __shfl_sync(kFullMask, k, 0), k1 = __shfl_sync(kFullMask, k, 1), k2 = __shfl_sync(kFullMask, k, 2),
-                      k3 = __shfl_sync(kFullMask, k, 3);
-            if (k0 == cur && k1 == cur && k2 == cur && k3 == cur) {
+                for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bvv[nt]);
+            if (tb == 0) {
+                const dbl4 bta = pick<NS>(o.b, ta);
+                const float4 cta = pick<NS>(o.c, ta);
+                const double vv[4] = {cta.x * bta.v[0] * inv_p, cta.y * bta.v[1] * inv_p, cta.z * bta.v[2] * inv_p, cta.w * bta.v[3] * inv_p};
+                const int k = o.k;
+                const int k0 = __shfl_sync(kFullMask, k, 0), k1 = __shfl_sync(kFullMask, k, 1), k2 = __shfl_sync(kFullMask, k, 2),
+                          k3 = __shfl_sync(kFullMask, k, 3);
+                if (k0 == cur && k1 == cur && k2 == cur && k3 == cur) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
-            } else {
+                    for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
+                } else {
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int kq = qq == 0 ? k0 : qq == 1 ? k1 : qq == 2 ? k2 : k3;
-                    if (kq < 0) continue;
-                    if (kq != cur) { flush(cur); cur = kq; }
-                    if (q == qq) {
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int kq = qq == 0 ? k0 : qq == 1 ? k1 : qq == 2 ? k2 : k3;
+                        if (kq < 0) continue;
+                        if (kq != cur) { flush(cur); cur = kq; }
+                        if (q == qq) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
+                            for (int i = 0; i < 4; ++i) gacc[i] += vv[i];
+                        }
                     }
                 }
             }
+        };
+        int2 rcN = load_rec(1);
+        Ops nxt = load_ops(load_rec(0));
+        for (int g = 0; g < ngrp; ++g) {
+            const Ops cu = nxt;
+            nxt = load_ops(rcN);
+            rcN = load_rec(g + 2);
+            process(cu);
         }
-    };
-    int2 rcN = load_rec(1);
-    Ops nxt = load_ops(load_rec(0));
-    for (int g = 0; g < ngrp; ++g) {
-        const Ops cu = nxt;
-        nxt = load_ops(rcN);
-        rcN = load_rec(g + 2);
-        process(cu);
-    }
-    if (tb == 0) flush(cur);
-    double *tile = tiles + (size_t)warp * 32 * 33;
-    store_acc(tile, acc, r, q);
-    __syncwarp();
-    double *Xp = w.Xpart + (size_t)slab * 64 * 64;
-    for (int x = lane; x < 1024; x += 32) {
-        const int i = x >> 5, j = x & 31;
-        Xp[(size_t)(32 * ta + i) * 64 + 32 * tb + j] = tile[i * 33 + j];
+        if (tb == 0) flush(cur);
+        __syncwarp();
+        store_acc(tile, acc, r, q);
+        __syncwarp();
+        for (int x = lane; x < 1024; x += 32) {
+            const int i = x >> 5, j = x & 31;
+            Xp[(size_t)(32 * ta + i) * MP + 32 * tb + j] = tile[i * 33 + j];
+        }
     }
     __syncthreads();
     if (gs_in_smem) {
-        double *gp = w.gspart + (size_t)slab * K * 64;
-        for (int x = tid; x < K * 64; x += kS64Warps * 32) gp[x] = gs[x];
+        double *gp = w.gspart + (size_t)slab * K * MP;
+        for (int x = tid; x < K * MP; x += kSTWarps * 32) gp[x] = gs[x];
     }
 }
 
-__global__ void __launch_bounds__(kS64Warps * 32, 2) k_stats64e(Model m, Plan p, Work w)
+template <int NS>
+__global__ void __launch_bounds__(kSTWarps * 32, 2) k_statsTe(Model m, Plan p, Work w)
 {
+    constexpr int MP = 32 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);                 // [4][32*33]
     const int item = blockIdx.x;
@@ -547,144 +573,168 @@ __global__ void __launch_bounds__(kS64Warps * 32, 2) k_stats64e(Model m, Plan p,
     const int2 *rec = p.erec + p.it_start[item];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
-    const int ta = warp >> 1, tb = warp & 1;
     double *tile = tiles + (size_t)warp * 32 * 33;
-    for (int x = lane; x < 32 * 33; x += 32) tile[x] = 0.0;
-    __syncwarp();
     const int ngrp = (n + 3) >> 2;
     const double sc = m.scale[e];
-    const double *pwbase = m.pwtab + (size_t)e * m.n_span * 64 + 4 * r;
+    const double *pwbase = m.pwtab + (size_t)e * m.n_span * MP + 4 * r;
+    double *Rp = w.Ritem + (size_t)item * MP * MP;
 
-    double G[4][4][2];
+    for (int tix = warp; tix < NS * NS; tix += kSTWarps) {
+        const int ta = tix / NS, tb = tix % NS;
+        __syncwarp();
+        for (int x = lane; x < 32 * 33; x += 32) tile[x] = 0.0;
+        __syncwarp();
+        double G[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) G[i][j][0] = G[i][j][1] = 0.0;
-    double dacc[4] = {0.0, 0.0, 0.0, 0.0};
-    double pwa[4] = {0.0, 0.0, 0.0, 0.0}, pwb[4] = {0.0, 0.0, 0.0, 0.0};   // run's pw on the tile's rows / columns (this lane's 4r..4r+3)
-    int mode = 0, run_sid = -1;
-    auto fold = [&]() {
-        if (mode == 0) return;
-        double pc[2][4];
+            for (int j = 0; j < 4; ++j) G[i][j][0] = G[i][j][1] = 0.0;
+        double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+        double pwa[4] = {0.0, 0.0, 0.0, 0.0}, pwb[4] = {0.0, 0.0, 0.0, 0.0};   // the run's pw on the tile's rows / columns
+        int mode = 0, run_sid = -1;
+        auto fold = [&]() {
+            if (mode == 0) return;
+            double pc[2][4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) pc[h][nt] = __shfl_sync(kFullMask, pwb[nt], 4 * (2 * q + h));
+                for (int nt = 0; nt < 4; ++nt) pc[h][nt] = __shfl_sync(kFullMask, pwb[nt], 4 * (2 * q + h));
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+                for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double wgt = mode == 1 ? pwa[mt] - pc[h][nt] : 1.0;
-                    double *dst = tile + (4 * r + mt) * 33 + 4 * (2 * q + h) + nt;
-                    *dst = fma(G[mt][nt][h], wgt, *dst);
-                    G[mt][nt][h] = 0.0;
-                }
-        mode = 0;
-    };
-    struct Ops { dbl4 uA, uB, wA, wB, pA, pB; double span; int sid; bool valid; };
-    auto load_rec = [&](int g) { return (g < ngrp && 4 * g + q < n) ? __ldg(rec + 4 * g + q) : make_int2(-1, 0); };
-    auto load_ops = [&](int2 rc) {
-        Ops o;
-        o.valid = rc.x >= 0;
-        o.sid = rc.y;
-        const int64_t gb = g0 + (o.valid ? rc.x : 0);
-        const double *up = w.uvec + (size_t)gb * 64 + 4 * r, *wp = w.bvec + (size_t)gb * 64 + 4 * r, *pp = pwbase + (size_t)rc.y * 64;
-        o.uA = ld4d(up); o.uB = ld4d(up + 32);
-        o.wA = ld4d(wp); o.wB = ld4d(wp + 32);
-        o.pA = ld4d(pp); o.pB = ld4d(pp + 32);
-        o.span = (double)__ldg(m.span_list + rc.y);
-        return o;
-    };
-    auto process = [&](const Ops &c) {
-        double dot = 0.0;
+                    for (int h = 0; h < 2; ++h) {
+                        const double wgt = mode == 1 ? pwa[mt] - pc[h][nt] : 1.0;
+                        double *dst = tile + (4 * r + mt) * 33 + 4 * (2 * q + h) + nt;
+                        *dst = fma(G[mt][nt][h], wgt, *dst);
+                        G[mt][nt][h] = 0.0;
+                    }
+            mode = 0;
+        };
+        struct Ops { dbl4 u[NS], w[NS], pw[NS]; double span; int sid; bool valid; };
+        auto load_rec = [&](int g) { return (g < ngrp && 4 * g + q < n) ? __ldg(rec + 4 * g + q) : make_int2(-1, 0); };
+        auto load_ops = [&](int2 rc) {
+            Ops o;
+            o.valid = rc.x >= 0;
+            o.sid = rc.y;
+            const int64_t gb = g0 + (o.valid ? rc.x : 0);
+            const double *up = w.uvec + (size_t)gb * MP + 4 * r, *wp = w.bvec + (size_t)gb * MP + 4 * r, *pp = pwbase + (size_t)rc.y * MP;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dot = fma(c.pA.v[i] * c.uA.v[i], c.wA.v[i], fma(c.pB.v[i] * c.uB.v[i], c.wB.v[i], dot));
-        dot = sum_over_r(c.valid ? dot : 0.0);
-        const double C = c.valid ? 1.0 / (sc * dot) : 0.0;
-        double uv[4], yv[4], pa[4], pb[4];
+            for (int x = 0; x < NS; ++x) { o.u[x] = ld4d(up + 32 * x); o.w[x] = ld4d(wp + 32 * x); o.pw[x] = ld4d(pp + 32 * x); }
+            o.span = (double)__ldg(m.span_list + rc.y);
+            return o;
+        };
+        auto process = [&](const Ops &c) {
+            double dot = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uv[i] = c.valid ? (ta ? c.uB.v[i] : c.uA.v[i]) : 0.0;
-            pa[i] = ta ? c.pB.v[i] : c.pA.v[i];
-            yv[i] = c.valid ? C * (tb ? c.wB.v[i] : c.wA.v[i]) : 0.0;
-            pb[i] = tb ? c.pB.v[i] : c.pA.v[i];
-        }
-        if (tb == 0) {                       // D_e on this tile's rows: y_a = C w_a with a in the ta half
+            for (int x = 0; x < NS; ++x)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dot = fma(c.pw[x].v[i] * c.u[x].v[i], c.w[x].v[i], dot);
+            dot = sum_over_r(c.valid ? dot : 0.0);
+            const double C = c.valid ? 1.0 / (sc * dot) : 0.0;
+            const dbl4 ua = pick<NS>(c.u, ta), pa4 = pick<NS>(c.pw, ta), wb = pick<NS>(c.w, tb), pb4 = pick<NS>(c.pw, tb);
+            double uv[4], yv[4], pa[4], pb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double ya = c.valid ? C * (ta ? c.wB.v[i] : c.wA.v[i]) : 0.0;
-                dacc[i] = fma(ya * uv[i], c.span * pa[i], dacc[i]);
+                uv[i] = c.valid ? ua.v[i] : 0.0;
+                pa[i] = pa4.v[i];
+                yv[i] = c.valid ? C * wb.v[i] : 0.0;
+                pb[i] = pb4.v[i];
             }
-        }
-        const int s0 = __shfl_sync(kFullMask, c.sid, 0);
-        const bool uni = __all_sync(kFullMask, !c.valid || c.sid == s0);
-        if (uni) {
-            if (mode != 1 || run_sid != s0) {
-                fold();
-                mode = 1;
-                run_sid = s0;
+            if (tb == 0) {                       // D_e on this tile's rows: y_a = C w_a with a in the ta part
+                const dbl4 wa = pick<NS>(c.w, ta);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    pwa[i] = __shfl_sync(kFullMask, pa[i], lane & ~3);    // block 0's rows
-                    pwb[i] = __shfl_sync(kFullMask, pb[i], lane & ~3);
+                    const double ya = c.valid ? C * wa.v[i] : 0.0;
+                    dacc[i] = fma(ya * uv[i], c.span * pa[i], dacc[i]);
                 }
             }
+            const int s0 = __shfl_sync(kFullMask, c.sid, 0);
+            const bool uni = __all_sync(kFullMask, !c.valid || c.sid == s0);
+            if (uni) {
+                if (mode != 1 || run_sid != s0) {
+                    fold();
+                    mode = 1;
+                    run_sid = s0;
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma884(G[mt][nt][0], G[mt][nt][1], uv[mt], yv[nt]);
-        } else {
-            if (mode != 2) { fold(); mode = 2; }
-            double xv[4], zv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { xv[i] = uv[i] * pa[i]; zv[i] = yv[i] * pb[i]; }
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    dmma884(G[mt][nt][0], G[mt][nt][1], xv[mt], yv[nt]);
-                    dmma884(G[mt][nt][0], G[mt][nt][1], -uv[mt], zv[nt]);
+                    for (int i = 0; i < 4; ++i) {
+                        pwa[i] = __shfl_sync(kFullMask, pa[i], lane & ~3);    // block 0's rows
+                        pwb[i] = __shfl_sync(kFullMask, pb[i], lane & ~3);
+                    }
                 }
-        }
-    };
-    int2 rcN = load_rec(1);
-    Ops nxt = load_ops(load_rec(0));
-    for (int g = 0; g < ngrp; ++g) {
-        const Ops cu = nxt;
-        nxt = load_ops(rcN);
-        rcN = load_rec(g + 2);
-        process(cu);
-    }
-    fold();
-    __syncwarp();
-    double *Rp = w.Ritem + (size_t)item * 64 * 64;
-    for (int x = lane; x < 1024; x += 32) {
-        const int i = x >> 5, j = x & 31;
-        Rp[(size_t)(32 * ta + i) * 64 + 32 * tb + j] = tile[i * 33 + j];
-    }
-    if (tb == 0) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const double dv = m.dsc[e * 64 + 32 * ta + 4 * r + mt];
-            const double v = sum_over_q(dacc[mt]) * (dv != 0.0 ? 1.0 / dv : 0.0);
-            if (q == 0) w.ditem[(size_t)item * 64 + 32 * ta + 4 * r + mt] = v;
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma884(G[mt][nt][0], G[mt][nt][1], uv[mt], yv[nt]);
+            } else {
+                if (mode != 2) { fold(); mode = 2; }
+                double xv[4], zv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { xv[i] = uv[i] * pa[i]; zv[i] = yv[i] * pb[i]; }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        dmma884(G[mt][nt][0], G[mt][nt][1], xv[mt], yv[nt]);
+                        dmma884(G[mt][nt][0], G[mt][nt][1], -uv[mt], zv[nt]);
+                    }
+            }
+        };
+        if constexpr (NS <= 2) {
+            int2 rcN = load_rec(1);
+            Ops nxt = load_ops(load_rec(0));
+            for (int g = 0; g < ngrp; ++g) {
+                const Ops cu = nxt;
+                nxt = load_ops(rcN);
+                rcN = load_rec(g + 2);
+                process(cu);
+            }
+        } else {
+            // 128 states: 3 x 4 x 256-bit operands per block do not fit twice next to the accumulators; only the records run ahead
+            int2 rcN = load_rec(0);
+            for (int g = 0; g < ngrp; ++g) {
+                const int2 rc = rcN;
+                rcN = load_rec(g + 1);
+                process(load_ops(rc));
+            }
+        }
+        fold();
+        __syncwarp();
+        for (int x = lane; x < 1024; x += 32) {
+            const int i = x >> 5, j = x & 31;
+            Rp[(size_t)(32 * ta + i) * MP + 32 * tb + j] = tile[i * 33 + j];
+        }
+        if (tb == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const double dv = m.dsc[e * MP + 32 * ta + 4 * r + mt];
+                const double v = sum_over_q(dacc[mt]) * (dv != 0.0 ? 1.0 / dv : 0.0);
+                if (q == 0) w.ditem[(size_t)item * MP + 32 * ta + 4 * r + mt] = v;
+            }
         }
     }
 }
 
-void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+template <int NS>
+static void launch_statsT_impl(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
-    const int in_smem = m.K <= kS64MaxKeysSmem ? 1 : 0;
-    const size_t smem = ((size_t)kS64Warps * 32 * 33 + (in_smem ? (size_t)m.K * 64 : 0)) * sizeof(double);
+    constexpr int MP = 32 * NS;
+    const int in_smem = (size_t)m.K * MP * sizeof(double) <= (size_t)kSTMaxGsBytes ? 1 : 0;
+    const size_t smem = ((size_t)kSTWarps * 32 * 33 + (in_smem ? (size_t)m.K * MP : 0)) * sizeof(double);
     static size_t configured = 0;
     if (configured < smem) {
-        cudaFuncSetAttribute(k_stats64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_statsT<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    k_stats64<<<p.n_slabs, kS64Warps * 32, smem, st>>>(m, p, w, in_smem);
-    if (p.n_items > 0) k_stats64e<<<p.n_items, kS64Warps * 32, (size_t)kS64Warps * 32 * 33 * sizeof(double), st>>>(m, p, w);
+    k_statsT<NS><<<p.n_slabs, kSTWarps * 32, smem, st>>>(m, p, w, in_smem);
+    if (p.n_items > 0) k_statsTe<NS><<<p.n_items, kSTWarps * 32, (size_t)kSTWarps * 32 * 33 * sizeof(double), st>>>(m, p, w);
+}
+
+void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st)   // Mp in {64, 128}
+{
+    if (m.Mp == 64) launch_statsT_impl<2>(m, p, w, st);
+    else launch_statsT_impl<4>(m, p, w, st);
 }
 
 size_t stats32_smem_bytes(const Model &m)
