@@ -156,3 +156,41 @@ def test_gpu_pipeline_errors():
     with pytest.raises(RuntimeError, match="w >= 1"):
         p.bin([2], 0)
     p.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Live pin (build container only): the oracle against the reference's own functions on random inputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isdir("/root/reference/smcpp"), reason="the reference tree is only mounted in the build container")
+def test_oracle_matches_live_reference_functions_on_random_inputs():
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_obs_golden", os.path.join(here, "golden", "make_obs_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    try:
+        et = mk.build_reference_cython()
+    except Exception as ex:   # no Cython / compiler on this box
+        pytest.skip(f"cannot build the reference's Cython module here: {ex}")
+    compress = mk.reference_function(os.path.join(mk.REF, "estimation_tools.py"), "compress_repeated_obs")
+    recode = mk.reference_function(os.path.join(mk.REF, "data_filter.py"), "_recode", cls="RecodeMonomorphic")
+    rng = np.random.default_rng(2024)
+    for case_no in range(60):
+        npop = int(rng.choice([1, 2]))
+        a = (2,) if npop == 1 else tuple(int(x) for x in rng.choice([(2, 0), (1, 1)]))
+        n = tuple(int(x) for x in rng.integers(1, 7, npop))
+        L = int(rng.choice([1, 3, 50, 800]))
+        thinning = int(rng.choice([1, 2, 9, 150, 4000]))
+        w = int(rng.choice([1, 4, 100, 1000]))
+        raw = mk.raw_rows(rng, L, npop, n, a, long_runs=bool(rng.integers(0, 2)))
+        # offset > 0 only on longer inputs: the reference sizes its output from data[offset:] (rows, :17), too small otherwise
+        offset = int(rng.choice([0, 1, thinning - 1])) if L >= 50 else 0
+        thin = et.thin_data(raw.copy(), thinning, offset)
+        assert np.array_equal(obsport.thin_data(raw, thinning, offset), thin), (case_no, "thin", offset)
+        c = mk.FakeContig(thin.copy(), a)
+        binned = np.array(et.bin_observations(c, w))
+        assert np.array_equal(obsport.bin_observations(thin, a, w), binned), (case_no, "bin")
+        c2 = mk.FakeContig(binned.copy(), a)
+        recode(None, c2)
+        assert np.array_equal(obsport.recode_monomorphic(binned, a), c2.data), (case_no, "recode")
+        assert np.array_equal(obsport.compress_repeated_obs(c2.data), compress(c2.data.copy())), (case_no, "compress")
