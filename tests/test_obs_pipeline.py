@@ -185,7 +185,11 @@ def test_oracle_matches_live_reference_functions_on_random_inputs():
         raw = mk.raw_rows(rng, L, npop, n, a, long_runs=bool(rng.integers(0, 2)))
         # offset > 0 only on longer inputs: the reference sizes its output from data[offset:] (rows, :17), too small otherwise
         offset = int(rng.choice([0, 1, thinning - 1])) if L >= 50 else 0
-        thin = et.thin_data(raw.copy(), thinning, offset)
+        try:
+            thin = et.thin_data(raw.copy(), thinning, offset)
+        except IndexError:      # the reference's own output buffer was too small for this offset: nothing to pin against
+            offset = 0
+            thin = et.thin_data(raw.copy(), thinning)
         assert np.array_equal(obsport.thin_data(raw, thinning, offset), thin), (case_no, "thin", offset)
         c = mk.FakeContig(thin.copy(), a)
         binned = np.array(et.bin_observations(c, w))
