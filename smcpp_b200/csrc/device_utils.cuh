@@ -3,7 +3,27 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <atomic>
+
 namespace smcb {
+
+// Kernel attributes (dynamic shared-memory limit, carve-out) are set per DEVICE, and one process may drive several
+// GPUs (one context per device, one host thread each): "already configured" flags are kept per device.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < kMaxDevices ? d : 0;
+}
+// true when this device still needs cudaFuncSetAttribute for `bytes` of dynamic shared memory; records the new size
+inline bool needs_smem_config(std::atomic<size_t> (&configured)[kMaxDevices], size_t bytes)
+{
+    std::atomic<size_t> &c = configured[current_device_slot()];
+    if (c.load(std::memory_order_relaxed) >= bytes && bytes > 0) return false;
+    c.store(bytes, std::memory_order_relaxed);
+    return true;
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {

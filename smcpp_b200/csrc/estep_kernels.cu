@@ -615,16 +615,15 @@ void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
     if (m.Mp == 64 || m.Mp == 128) { launch_stats64(m, p, w, st); return; }
     const int smem = stats_smem_bytes(m);
     // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
-    static int configured[5] = {0, 0, 0, 0, 0};
+    static std::atomic<size_t> configured[5][kMaxDevices];
     const int r = m.Mp / 32;
-    if (configured[r] < smem) {
+    if (needs_smem_config(configured[r], (size_t)smem)) {
         switch (r) {
         case 1: cudaFuncSetAttribute(k_stats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         case 2: cudaFuncSetAttribute(k_stats<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         case 3: cudaFuncSetAttribute(k_stats<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         default: cudaFuncSetAttribute(k_stats<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
         }
-        configured[r] = smem;
     }
     switch (r) {
     case 1: k_stats<2><<<p.n_slabs, kStatThreads, smem, st>>>(m, p, w); break;

@@ -732,9 +732,8 @@ static void set_attrs(KF kernel, size_t smem)
 
 static void configure_once()
 {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static std::atomic<size_t> done[kMaxDevices];
+    if (!needs_smem_config(done, 1)) return;
     set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg, 4));
     set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared, 4));
     set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));

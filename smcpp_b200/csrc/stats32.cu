@@ -722,11 +722,8 @@ static void launch_statsT_impl(const Model &m, const Plan &p, const Work &w, cud
     constexpr int MP = 32 * NS;
     const int in_smem = (size_t)m.K * MP * sizeof(double) <= (size_t)kSTMaxGsBytes ? 1 : 0;
     const size_t smem = ((size_t)kSTWarps * 32 * 33 + (in_smem ? (size_t)m.K * MP : 0)) * sizeof(double);
-    static size_t configured = 0;
-    if (configured < smem) {
-        cudaFuncSetAttribute(k_statsT<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static std::atomic<size_t> configured[kMaxDevices];
+    if (needs_smem_config(configured, smem)) cudaFuncSetAttribute(k_statsT<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_statsT<NS><<<p.n_slabs, kSTWarps * 32, smem, st>>>(m, p, w, in_smem);
     if (p.n_items > 0) k_statsTe<NS><<<p.n_items, kSTWarps * 32, (size_t)kSTWarps * 32 * 33 * sizeof(double), st>>>(m, p, w);
 }
@@ -747,19 +744,13 @@ size_t stats32_smem_bytes(const Model &m)
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
     const size_t smem = stats32_smem_bytes(m);
-    static size_t configured = 0;
-    if (configured < smem) {
-        cudaFuncSetAttribute(k_stats32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static std::atomic<size_t> configured[kMaxDevices];
+    if (needs_smem_config(configured, smem)) cudaFuncSetAttribute(k_stats32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w, m.K <= kS32MaxKeysSmem ? 1 : 0);
     if (p.n_items > 0) {
         const size_t smem_e = ((size_t)kSEWarps * 32 * 33 + (size_t)kSEWarps * 32) * sizeof(double);
-        static bool configured_e = false;
-        if (!configured_e) {
-            cudaFuncSetAttribute(k_stats32e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
-            configured_e = true;
-        }
+        static std::atomic<size_t> configured_e[kMaxDevices];
+        if (needs_smem_config(configured_e, smem_e)) cudaFuncSetAttribute(k_stats32e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
         k_stats32e<<<p.n_items, kSEWarps * 32, smem_e, st>>>(m, p, w);
     }
 }
