@@ -11,13 +11,16 @@ sharded over the ranks (strong scaling) and one NCCL SUM all-reduce of the packe
 Model inputs (pi, transition, emission table) come from tests/golden/model_C3.npz, which the unmodified
 reference produced for this exact workload; observations are synthetic (smcpp_b200/synth.py).
 
-`value`  : blocks/s with everything resident in HBM (per-step inputs included), wall time of K steps
-           bracketed by barrier + synchronize, max over ranks.
-`e2e`    : the same through the host-facing C ABI call (host buffers: eigensystems computed by the library, per-step
-           inputs H2D, all per-contig results D2H inside the timed region) + the all-reduce.
-`roofline`: recursion kernels (k_forward || k_backward, the dominant phase) against the measured HBM peak,
+`value`  : blocks/s of the whole reference Estep (eigensystems of diag(e_key) Td^T + operand tables + recursions + statistics +
+           reduction + all-reduce) with the observations resident in HBM and the results left on the device; wall time of
+           K steps bracketed by barrier + synchronize, max over ranks.
+`e2e`    : the same through the host-facing C ABI call with HOST buffers (per-step inputs H2D, all per-contig results D2H
+           inside the timed region) + the all-reduce + a D2H read of the reduced statistics.
+`roofline`: the recursion kernel (forward + backward pass in one launch, the dominant phase) against the measured HBM peak,
            algorithmic bytes of SURVEY 8d; `roofline_fp64` relates the algorithmic flops to the measured
            FP64 FMA peak of this GPU, which is the bound that binds at M = 32.
+`parity` : the reference's sample run (cpu_baseline leg) against the CUDA path on the same contigs (loglik delta vs ref).
+`sweep`  : the other BASELINE configs on one GPU (C2, C4, C5-16/32/64/128) with both roofline fractions.
 """
 import argparse
 import json
@@ -141,9 +144,75 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def relmax(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())
+
+
+def parity_block(capi, device, w, ref, what):
+    """The reference's sample run (oracle/_ref) against the CUDA path on the same contigs: default planner, library
+    eigensystems, the reference's own pi / T / emission table as inputs."""
+    ctx = capi.Context(device)
+    ctx.set_contigs(w.contigs, w.npop, ref["keys"])
+    out = ctx.estep(ref["pi"], ref["T"], ref["E"], None)
+    st = ctx.stats()
+    ctx.close()
+    nc = len(w.contigs)
+    return {"ll_rel_vs_reference": abs(float(out["ll"].sum()) - float(ref["ll"].sum())) / abs(float(ref["ll"].sum())),
+            "ll_rel_worst_contig": float(np.max(np.abs(out["ll"] - ref["ll"]) / np.abs(ref["ll"]))),
+            "xisum_rel": max(relmax(out["xisum"][c], ref["xisum"][c]) for c in range(nc)),
+            "gamma_sums_rel": max(relmax(out["gamma_sums"][c], ref["gamma_sums"][c]) for c in range(nc)),
+            "gamma0_rel": max(relmax(out["gamma0"][c], ref["gamma0"][c]) for c in range(nc)),
+            "tolerance": {"ll_rel": 1e-8, "stats_rel_to_largest_entry": 1e-7},
+            "planner": f"default: {st['n_chunks']} chunks x {st['chunk_blocks']} blocks, burn-in {st['burn_in_blocks']}",
+            "on": f"oracle/_ref/ref_harness (unmodified reference sources) vs smcpp_b200_estep on {what}; full-size pins: tests/test_headline_parity.py"}
+
+
+def sweep_block(capi, device, hbm_peak, fp64_peak, steps=5):
+    """The other BASELINE configs on one GPU (device times from CUDA events inside the library, whole E-step including
+    the library's eigensystems): ms, blocks/s and both roofline fractions per state count (BASELINE config 5)."""
+    res = {}
+    for cfg in ("C2", "C4", "C5-16", "C5-32", "C5-64", "C5-128"):
+        C, L, M, n, P = workload_spec(cfg)
+        model = load_model(cfg)
+        contigs = [synth.make_contig(L, n, 1000 + c, P) for c in range(C)]
+        ctx = capi.Context(device)
+        ctx.set_contigs(contigs, P, model["keys"])
+        for _ in range(3):
+            ctx.estep_device(model["pi"], model["T"], model["E"], None, upload=True)
+        ms = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.estep_device(model["pi"], model["T"], model["E"], None, upload=True)
+            ms.append(ctx.stats()["ms_total"])
+        wall = (time.perf_counter() - t0) / steps
+        st = ctx.stats()
+        ctx.close()
+        blocks = C * L
+        dev = float(np.median(ms)) * 1e-3
+        res[cfg] = {"M": M, "blocks": blocks, "device_ms": 1e3 * dev, "wall_ms": 1e3 * wall, "blocks_per_s": blocks / wall,
+                    "hbm_frac": alg_bytes_per_block(M, P) * blocks / dev / 1e9 / hbm_peak,
+                    "fp64_frac": alg_flops_per_block(M) * blocks / dev / 1e12 / fp64_peak,
+                    "chunks": f"{st['n_chunks']}x{st['chunk_blocks']}"}
+    return res
+
+
+def measured_traffic(cfg, world):
+    """dram__bytes_read + dram__bytes_write per E-step from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(cfg, {}).get(str(world))
+    if not d:
+        return None, None
+    return d.get("dominant_kernel_bytes"), d
+
+
 def reference_arm(args, cfg, rank, world):
-    """The reference's own CPU implementation of the path (oracle/_ref/ref_harness = the unmodified
-    reference sources) on the host cores, on a bounded sample of the same workload."""
+    """The reference's own CPU implementation of the path (oracle/_ref/ref_harness = the unmodified reference sources) on
+    the host cores.  The K timed steps run on a bounded sample of the workload (every contig cut to --ref-sample-blocks
+    blocks: the reference needs ~40 us per block and thread, a full-length step takes over a minute); at --gpus 1 one
+    FULL-LENGTH step (1 warm-up + --ref-full-steps timed) is run as well and reported under `full_length`, so the
+    per-block rate of the sample can be checked against the real configuration."""
     if rank != 0:
         return 0
     from oracle import refrun
@@ -161,12 +230,25 @@ def reference_arm(args, cfg, rank, world):
     blocks = w.total_blocks * len(secs)
     val = blocks / t
     sample = f"{C} contigs x {sample_L} blocks (1/{max(1, L // sample_L)} of each contig), M={M}, {threads} OpenMP threads"
+    full = None
+    if args.gpus == 1 and args.ref_full_steps > 0 and sample_L < L:
+        try:
+            wf = synth.make_workload(cfg, C, L, M, n, npop=P)
+            of = refrun.run(wf, threads=threads, repeat=1 + args.ref_full_steps)
+            fs = [float(x) for x in of["estep_seconds"][1:]]
+            full = {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n} (full length)", "steps": len(fs), "warmup": 1,
+                    "ms_per_step": 1e3 * float(np.mean(fs)), "value": wf.total_blocks / float(np.mean(fs)), "unit": "blocks/s",
+                    "threads": threads, "loglik": float(of["ll"].sum()),
+                    "sample_rate_over_full_rate": val / (wf.total_blocks / float(np.mean(fs)))}
+        except Exception as ex:  # the confirmation run must never break the line
+            full = {"failed": str(ex)[:200]}
     line = {"impl": "reference", "metric": "E-step observation-blocks/sec", "value": val, "unit": "blocks/s", "n_gpus": args.gpus,
             "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1e3 * t / len(secs), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 (float alpha_hat storage)", "data": "synthetic",
-            "config": {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n}", "sample": sample},
+            "config": {"workload": f"{cfg}: {C} contigs x {L} RLE blocks, M={M}, n={n}, contigs sharded over ranks", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "blocks/s", "cores": threads, "kind": "reference", "sample": sample,
                              "host_cores": cores},
+            "full_length": full,
             "e2e": {"value": val, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -180,7 +262,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--ref-sample-blocks", type=int, default=50_000)
+    ap.add_argument("--ref-full-steps", type=int, default=1, help="reference arm, --gpus 1: timed FULL-LENGTH steps (after 1 warm-up); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the per-config sweep block (C2, C4, C5-*)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = args.workload
@@ -217,7 +301,6 @@ def main():
     upload_s = time.time() - t0
     nred = 1 + M + M * M + K * M
     red = torch.zeros(nred, dtype=torch.float64, device="cuda")
-    eig = model   # the reference's eigensystems for this model (bit-identical inputs on both arms)
 
     def barrier():
         if world > 1:
@@ -226,7 +309,9 @@ def main():
 
     def step_resident():
         if contigs:
-            ctx.estep_device(model["pi"], model["T"], model["E"], eig, upload=False)
+            # the whole of the reference's Estep: eigensystems of diag(e_key) Td^T (TransitionBundle::update), operand tables,
+            # recursions, statistics, reduction; the observations and work buffers are resident, results stay on the device
+            ctx.estep_device(model["pi"], model["T"], model["E"], None, upload=True)
             ctx.copy_reduced_to_device(red.data_ptr(), nred)      # D2D on the context's stream, synchronised
         else:
             red.zero_()
@@ -248,8 +333,6 @@ def main():
         return red.cpu()                                          # D2H read of the reduced statistics (synchronises)
 
     # ---- warm-up (also uploads the per-step inputs once for the resident arm)
-    if contigs:
-        ctx.estep_device(model["pi"], model["T"], model["E"], eig, upload=True)
     for _ in range(args.warmup):
         step_resident()
     launches_per_step = ctx.stats()["kernel_launches"] if contigs else 0
@@ -257,13 +340,14 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    ms_rec, ms_tot = [], []
+    ms_rec, ms_tot, ms_sta = [], [], []
     for _ in range(args.steps):
         step_resident()
         if contigs:
             st = ctx.stats()
             ms_rec.append(st["ms_forward"])
             ms_tot.append(st["ms_total"])
+            ms_sta.append(st["ms_stats"])
     barrier()
     t_res = time.perf_counter() - t0
     ll_total = float(red[0].item())
@@ -298,6 +382,7 @@ def main():
         ach = alg_bytes_per_block(M, P) * my_blocks / (rec_ms * 1e-3) / 1e9
         fp64_peak = ctx.fp64_peak_tflops()
         ach_f = alg_flops_per_block(M) * my_blocks / (tot_ms * 1e-3) / 1e12
+        traffic, traffic_detail = measured_traffic(cfg, world)
         h2d = 8 * (M + M * M + K * M + len(model["eig_scale"]) * (2 * M * M + 2 * M + 1))
         d2h = 8 * (len(owned) * (1 + M + M * M + K * M) + nred)
         line = {
@@ -312,19 +397,21 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
             "e2e": {"value": e2e, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "device_ms_per_step": e2e_stats.get("ms_total")},
-            "roofline": {"bound": "hbm", "kernel": "k_forward || k_backward (recursions, rank 0)", "achieved": ach, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach / hbm_peak,
-                         # dram__bytes_read+write of k_forward_mma + k_backward_mma, one launch each (profiles/r1h_summary.md);
-                         # measured for this workload on one GPU only
-                         "traffic": 11.80e9 if (cfg == "C3" and world == 1) else None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_recursions_mma (forward + backward recursion in one launch, rank 0)", "achieved": ach,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         # dram__bytes_read + dram__bytes_write of that kernel / of all kernels of one E-step (ncu, profiles/)
+                         "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
                          "alg_bytes_per_block": alg_bytes_per_block(M, P), "kernel_ms": rec_ms,
-                         "kernel_ms_per_step": [round(float(x), 3) for x in ms_rec]},
+                         "kernel_ms_per_step": [round(float(x), 3) for x in ms_rec],
+                         "phases_ms": {"recursions": rec_ms, "statistics": float(np.mean(ms_sta)) if ms_sta else None, "estep": tot_ms}},
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
                               "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},
             "loglik": ll_total, "loglik_allreduce_check_rel": abs(ll_total - ll_check) / abs(ll_check), "chunks": ctx.stats()["n_chunks"], "sweeps": [ctx.stats()["fwd_sweeps"], ctx.stats()["bwd_sweeps"]],
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
+            # reference on the host cores (bounded sample) + the SAME sample through the GPU path with the default planner:
+            # the metric's "loglik delta vs ref" (BASELINE.json) in the driver-run line
             try:
                 from oracle import refrun
                 if refrun.available():
@@ -333,15 +420,23 @@ def main():
                     sL = min(L, args.ref_sample_blocks)
                     w = synth.make_workload(cfg, C, sL, M, n, npop=P)
                     o = refrun.run(w, threads=threads, repeat=2)
-                    s = float(o["estep_seconds"][-1])
-                    line["cpu_baseline"] = {"value": w.total_blocks / s, "unit": "blocks/s", "cores": threads, "kind": "reference",
-                                            "sample": f"{C} contigs x {sL} blocks, {threads} OpenMP threads of {cores} host cores",
-                                            "seconds": s}
-                else:
+                    sec = float(o["estep_seconds"][-1])
+                    what = f"{C} contigs x {sL} blocks, {threads} OpenMP threads of {cores} host cores"
+                    if world == 1:
+                        line["cpu_baseline"] = {"value": w.total_blocks / sec, "unit": "blocks/s", "cores": threads, "kind": "reference",
+                                                "sample": what, "seconds": sec}
+                    line["parity"] = parity_block(capi, local_rank, w, o, what)
+                elif world == 1:
                     line["cpu_baseline"] = {"value": None, "unit": "blocks/s", "cores": 0, "kind": "reference",
                                             "sample": "oracle/_ref not built on this box"}
             except Exception as ex:  # the baseline must never break the bench line
                 line["cpu_baseline"] = {"value": None, "unit": "blocks/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        if world == 1 and not args.no_sweep:
+            try:
+                ctx.close()
+                line["sweep"] = sweep_block(capi, local_rank, hbm_peak, fp64_peak)
+            except Exception as ex:
+                line["sweep"] = {"failed": str(ex)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

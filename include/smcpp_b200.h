@@ -38,7 +38,11 @@ const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx); /* ctx may be NULL
 
 /* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks" (both passes), "burn_in_blocks_forward", "target_warps", "slab_blocks", "fwd_tol",
  * "fwd_tol_burn_in", "bwd_tol", "max_sweeps", "force_sequential", "mma_min_chunks", "force_mma_forward", "chunks_per_warp",
- * "fwd_cached_keys"} (the last two are process-wide and exist for tests / experiments).
+ * "fwd_cached_keys", "fused_recursions"} (all per context; the last three exist for tests / experiments).
+ * Note on "fwd_tol_burn_in" (default 1e-6): the forward pass of a chunk starts from a burn-in over the preceding blocks and
+ * is accepted when its float alpha_hat start agrees with the neighbour chunk's end to this relative tolerance -- the noise
+ * floor of two float trajectories with different histories.  This is an approximation the reference does not make; it is
+ * what keeps the log-likelihood within ~1e-11 relative instead of bit-identical ("force_sequential" = 1 gives the literal chain).
  * Returns non-zero for an unknown name. */
 int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value);
 
@@ -208,6 +212,7 @@ typedef struct smcpp_b200_stats_t {
     double fwd_max_mismatch, bwd_max_mismatch;
     float ms_forward_only;         /* forward pass 0 alone; ms_forward = both recursions incl. sweeps, ms_backward = backward pass 0 alone */
     int32_t mma_rounds, mma_steps; /* tensor-path forward kernel: warp rounds and committed chunk-steps (efficiency = steps / (8 rounds)) */
+    int32_t converged;             /* 0: the repair sweeps hit max_sweeps with chunk boundaries still failing -- estep() returned an error */
 } smcpp_b200_stats_t;
 int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out);
 

@@ -20,7 +20,7 @@ using namespace smcb;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // error text of the last failed create() on this thread
 
 struct KeyRow {
     std::array<int32_t, 6> v;
@@ -88,17 +88,17 @@ struct smcpp_b200_ctx {
     std::vector<int32_t> eig_of_key;  // K
     std::vector<uint8_t> present;     // C x K
     std::vector<int32_t> h_span, h_span_id, span_list;
-    std::vector<uint16_t> h_key;     // packed code: key id | (1 + eigen index) << 11 for span > 1 blocks
+    std::vector<kcode_t> h_key;     // packed code: key id | (1 + eigen index) << kKeyBits for span > 1 blocks
     int hot_eig = -1;
     int hot_keys[4] = {-1, -1, -1, -1};   // most frequent span-1 keys (the forward kernel keeps their step matrices in shared memory)
     DevBuf<int32_t> d_span, d_span_id, d_span_list;
     DevBuf<double> m_pwtab, m_pwq, m_invdiff, w_gamma;
     DevBuf<int64_t> d_gcol_off;
     bool save_gamma = false, gamma_valid = false;
-    DevBuf<uint16_t> d_key;
+    DevBuf<kcode_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
-    DevBuf<uint32_t> d_sl_mask;
+    DevBuf<uint32_t> d_sl_mask, d_ct_mask;
     DevBuf<int2> d_srec, d_erec;
     DevBuf<int32_t> d_seg, d_it_len, d_it_contig, d_it_eig, d_it_off;
     DevBuf<int64_t> d_it_start;
@@ -129,6 +129,7 @@ struct smcpp_b200_ctx {
     int opt_force_mma_forward = 0;  // tests: take the tensor-path forward kernel even where mma_forward_pays() says no
     int opt_mma_min_chunks = 64;    // use the 8-chunks-per-warp tensor-path recursions from this many chunks on
     int burn_in_adapt = 0;          // grows when boundary checks fail (sticky between E-steps)
+    RecOpts rec;                    // tensor-path recursion tuning (chunks per warp, resident step matrices)
 
     // ---- plan
     bool plan_valid = false;
@@ -155,6 +156,9 @@ struct smcpp_b200_ctx {
     PinBuf<int> h_counters;
     PinBuf<double> h_out;
     std::vector<double> eig_store;  // library-computed eigensystems of the last estep
+    std::vector<int32_t> eig_cplx;  // per eigen key: the spectrum had a complex pair (library-computed eigensystems)
+    std::vector<int64_t> gcol_off;  // first posterior column of each contig (save_gamma)
+    bool pending = false;           // an E-step is enqueued and its boundary counters have not been looked at yet
 
     smcpp_b200_stats_t stats = {};
 
@@ -184,7 +188,7 @@ struct smcpp_b200_ctx {
         p.span = d_span.p; p.kcode = d_key.p; p.span_id = d_span_id.p;
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
         p.ch_contig = d_ch_contig.p; p.ch_start = d_ch_start.p; p.ch_len = d_ch_len.p;
-        p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p;
+        p.sl_contig = d_sl_contig.p; p.sl_start = d_sl_start.p; p.sl_len = d_sl_len.p; p.sl_mask = d_sl_mask.p; p.ct_mask = d_ct_mask.p; p.mask_words = (1 + n_eig + 31) / 32;
         p.srec = d_srec.p; p.seg = d_seg.p;
         p.n_items = n_items; p.erec = d_erec.p; p.it_start = d_it_start.p; p.it_len = d_it_len.p; p.it_contig = d_it_contig.p;
         p.it_eig = d_it_eig.p; p.it_off = d_it_off.p;
@@ -219,9 +223,22 @@ static int fail(smcpp_b200_ctx *ctx, const std::string &msg)
     return 1;
 }
 
+// Entry points run on the context's device and leave the caller's current device as they found it (a host program
+// -- torch, or several contexts in one process -- has its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
-int smcpp_b200_abi_version(void) { return 1; }
+int smcpp_b200_abi_version(void) { return 2; }
 
 int smcpp_b200_create(smcpp_b200_ctx **out, int device)
 {
@@ -240,6 +257,7 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device)
     }
     smcpp_b200_ctx *ctx = new smcpp_b200_ctx();
     ctx->device = device;
+    DeviceGuard guard(device);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
@@ -260,13 +278,14 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device)
 void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
+    DeviceGuard guard(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->st2) cudaStreamSynchronize(ctx->st2);
     // DevBuf / PinBuf members are released explicitly (they are plain structs without destructors)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_pwq.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
+    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
     ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
@@ -307,8 +326,9 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
     else if (n == "force_mma_forward") ctx->opt_force_mma_forward = value != 0;
     else if (n == "mma_min_chunks") ctx->opt_mma_min_chunks = std::max(1, (int)value);
-    else if (n == "chunks_per_warp") smcb::set_chunks_per_warp((int)value);   // process-wide, 0 = automatic
-    else if (n == "fwd_cached_keys") smcb::set_fwd_cached_keys((int)value);   // process-wide (sizes the kernel's shared memory)
+    else if (n == "chunks_per_warp") ctx->rec.force_G = (int)value;           // 0 = automatic
+    else if (n == "fwd_cached_keys") ctx->rec.cached_keys = std::max(0, std::min(4, (int)value));
+    else if (n == "fused_recursions") ctx->rec.fused = value != 0;
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;
@@ -320,7 +340,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     if (!ctx) return 1;
     if (n_contigs <= 0 || !obs || !lengths) return fail(ctx, "set_contigs: no contigs");
     if (npop < 1 || npop > 2) return fail(ctx, "set_contigs: npop must be 1 or 2");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     ctx->contigs_ok = false;
     ctx->plan_valid = false;
     const int W = 1 + 3 * npop, Q = 3 * npop;
@@ -368,7 +388,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
             return std::lexicographical_compare(a.v.begin(), a.v.begin() + Q, b.v.begin(), b.v.begin() + Q);
         });
     }
-    if (table.size() > 2047) return fail(ctx, "set_contigs: more than 2047 distinct observation keys");
+    if (table.size() > (size_t)kMaxKeys) return fail(ctx, "set_contigs: more than 65535 distinct observation keys");
     const int K = (int)table.size();
     ctx->K = K;
     ctx->keys.assign((size_t)K * Q, 0);
@@ -393,7 +413,6 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
         }
     }
     ctx->n_eig = (int)ctx->eig_keys.size();
-    if (ctx->n_eig > kMaxEig) return fail(ctx, "set_contigs: more than 30 distinct keys occur with span > 1");
     // pass 2: per-block span / key id, per-contig presence
     ctx->h_span.resize(ctx->total);
     ctx->h_key.resize(ctx->total);
@@ -425,7 +444,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
                 }
                 ctx->h_span_id[g0 + l] = it->second;
             }
-            ctx->h_key[g0 + l] = (uint16_t)(last_id | ((e + 1) << 11));
+            ctx->h_key[g0 + l] = (kcode_t)last_id | ((kcode_t)(e + 1) << kKeyBits);
             if (e >= 0) ++eig_count[e];
             if (row[0] == 1) ++site_count[last_id];
             ctx->present[(size_t)c * K + last_id] = 1;
@@ -443,7 +462,7 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     CU(ctx->d_span.ensure(ctx->total));
     CU(ctx->d_key.ensure(ctx->total));
     CU(cudaMemcpy(ctx->d_span.p, ctx->h_span.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_key.p, ctx->h_key.data(), ctx->total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_key.p, ctx->h_key.data(), ctx->total * sizeof(kcode_t), cudaMemcpyHostToDevice));
     if (ctx->span_list.empty()) ctx->span_list.push_back(2);   // keeps the table non-empty; never referenced
     CU(ctx->d_span_id.ensure(ctx->total));
     CU(cudaMemcpy(ctx->d_span_id.p, ctx->h_span_id.data(), ctx->total * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -534,7 +553,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             const int per_layer = ctx->n_sm * 32;
             // inputs too small to fill the warps with 8 chunks each keep the burn-in as the lower bound
             if (chunks_for(min_lc_for(per_layer)) < ctx->n_sm * 8) relaxed = false;
-            const int layers = std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp), ctx->n_sm * 8) / (ctx->n_sm * 4)));
+            const int layers = std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp, ctx->rec), ctx->n_sm * 8) / (ctx->n_sm * 4)));
             const double step_cost[3] = {0.0, 3750.0, 5460.0};
             double best = 0.0;
             Lc = 0;
@@ -559,13 +578,15 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M;
     ctx->plan_burn = burn;
     if (same) return 0;
-    CU(cudaSetDevice(ctx->device));
+    ctx->plan_valid = false;   // a failure below must not leave the previous plan looking current
+    DeviceGuard guard(ctx->device);
     const int C = ctx->C;
     ctx->chunk_off.assign(C + 1, 0);
     ctx->slab_off.assign(C + 1, 0);
     ctx->col_off.assign(C, 0);
     std::vector<int32_t> ch_contig, ch_start, ch_len, sl_contig, sl_start, sl_len;
-    std::vector<uint32_t> sl_mask;
+    const int MW = (1 + ctx->n_eig + 31) / 32;
+    std::vector<uint32_t> sl_mask, ct_mask((size_t)ctx->C * MW, 0u), mask(MW);
     std::vector<int2> srec(ctx->total);
     std::vector<int32_t> seg;
     std::vector<uint64_t> sortbuf;
@@ -585,22 +606,22 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         const int nsl = (int)((L + slab - 1) / slab);
         for (int i = 0; i < nsl; ++i) {
             const int s0 = i * slab, n = (int)std::min<int64_t>(slab, L - (int64_t)i * slab);
-            uint32_t mask = 0;
+            std::fill(mask.begin(), mask.end(), 0u);
             const int64_t g0 = ctx->blk_off[c] + s0;
             for (int b = 0; b < n; ++b) {
-                const int code = ctx->h_key[g0 + b] >> 11;
-                mask |= code == 0 ? 1u : (2u << (code - 1));
+                const int code = (int)(ctx->h_key[g0 + b] >> kKeyBits);   // bit 0: span 1, bit 1 + e: eigen key e
+                mask[code >> 5] |= 1u << (code & 31);
             }
             sl_contig.push_back(c);
             sl_start.push_back(s0);
             sl_len.push_back(n);
-            sl_mask.push_back(mask);
+            for (int x = 0; x < MW; ++x) { sl_mask.push_back(mask[x]); ct_mask[(size_t)c * MW + x] |= mask[x]; }
             // processing order of the statistics kernel: span-1 blocks sorted by key, then each eigen key's blocks
             sortbuf.clear();
             for (int b = 0; b < n; ++b) {
-                const uint16_t kc = ctx->h_key[g0 + b];
-                const uint64_t cls = kc >> 11;   // 0 = span 1, 1 + e otherwise
-                const uint64_t key = cls == 0 ? (kc & 2047) : 0;
+                const kcode_t kc = ctx->h_key[g0 + b];
+                const uint64_t cls = kc >> kKeyBits;   // 0 = span 1, 1 + e otherwise
+                const uint64_t key = cls == 0 ? (kc & kKeyMask) : 0;
                 sortbuf.push_back((cls << 48) | (key << 32) | (uint32_t)(s0 + b));
             }
             std::sort(sortbuf.begin(), sortbuf.end());
@@ -612,8 +633,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             seg.push_back((int32_t)at);
             for (int b = 0; b < n; ++b) {
                 const int32_t bi = (int32_t)(sortbuf[b] & 0xffffffffu);
-                const uint16_t kc = ctx->h_key[ctx->blk_off[c] + bi];
-                srec[g0 + b] = make_int2(bi, (kc >> 11) == 0 ? (int)(kc & 2047) : ctx->h_span_id[ctx->blk_off[c] + bi]);
+                const kcode_t kc = ctx->h_key[ctx->blk_off[c] + bi];
+                srec[g0 + b] = make_int2(bi, (kc >> kKeyBits) == 0 ? (int)(kc & kKeyMask) : ctx->h_span_id[ctx->blk_off[c] + bi]);
             }
         }
         ctx->slab_off[c + 1] = (int)sl_contig.size();
@@ -634,14 +655,14 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             // one counting sort over (eigen key, span id)
             cnt.assign((size_t)NEp * NS + 1, 0);
             for (int64_t b = 0; b < L; ++b) {
-                const int cls = ctx->h_key[g0 + b] >> 11;
+                const int cls = ctx->h_key[g0 + b] >> kKeyBits;
                 if (cls) ++cnt[(size_t)(cls - 1) * NS + ctx->h_span_id[g0 + b] + 1];
             }
             for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
             const size_t base = erec.size();
             erec.resize(base + (size_t)cnt.back());
             for (int64_t b = 0; b < L; ++b) {
-                const int cls = ctx->h_key[g0 + b] >> 11;
+                const int cls = ctx->h_key[g0 + b] >> kKeyBits;
                 if (cls) {
                     const int sid = ctx->h_span_id[g0 + b];
                     erec[base + (size_t)cnt[(size_t)(cls - 1) * NS + sid]++] = make_int2((int)b, sid);
@@ -684,6 +705,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     UP(d_sl_start, sl_start);
     UP(d_sl_len, sl_len);
     UP(d_sl_mask, sl_mask);
+    UP(d_ct_mask, ct_mask);
     UP(d_srec, srec);
     UP(d_seg, seg);
     if (ctx->n_items) {
@@ -762,15 +784,48 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     return 0;
 }
 
+// ---- one E-step = enqueue everything, then ONE host synchronisation ---------------------------------------------
+// The boundary checks of the chunked recursions almost always pass, so the statistics and the closing kernels are
+// enqueued right behind them and the counters travel back with the results; only when a check failed does the host
+// run the repair sweeps and redo the statistics (complete_estep).  No host synchronisation sits between the kernels of
+// the common path (round 1 had three: after setup, after the checks, before the posterior kernel).
+static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, const Plan &p, const Work &w)
+{
+    cudaEventRecord(ctx->ev[2], ctx->st);
+    launch_stats(m, p, w, ctx->st);
+    cudaEventRecord(ctx->ev[3], ctx->st);
+    ctx->stats.kernel_launches += ((m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0) ? 2 : 1;
+    ctx->gamma_valid = false;
+    if (ctx->save_gamma) {
+        // full posterior decoding (reference saveGamma, src/hmm.cpp:48-49,147-148): M x (L+1) doubles per contig
+        launch_posterior(ctx->model(), p, w, ctx->w_gamma.p, ctx->d_gcol_off.p, ctx->n_sm, ctx->st);
+        ctx->stats.kernel_launches += 2;
+        ctx->gamma_valid = true;
+    }
+    launch_finalize(m, p, w, ctx->st);
+    ctx->stats.kernel_launches += 3;
+    cudaEventRecord(ctx->ev[4], ctx->st);
+    cudaMemcpyAsync(ctx->h_counters.p, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st);
+}
+
 static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_eig,
                      const double *P, const double *Pinv, const double *d, const double *dsc, const double *scale,
                      bool upload)
 {
     if (ctx->C == 0 || !ctx->contigs_ok) return fail(ctx, "estep: set_contigs() has not been called (or failed)");
     if (M < 1 || M > kMaxMp) return fail(ctx, "estep: M must be in [1, 128]");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     if (make_plan(ctx, M)) return 1;
     const int K = ctx->K, NE = ctx->n_eig;
+    ctx->pending = false;
+    if (ctx->save_gamma) {
+        ctx->gcol_off.assign(ctx->C + 1, 0);     // member: the asynchronous copy below reads it after this function returns
+        for (int c = 0; c < ctx->C; ++c) ctx->gcol_off[c + 1] = ctx->gcol_off[c] + (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
+        CU(ctx->w_gamma.ensure((size_t)ctx->gcol_off[ctx->C] * M));
+        CU(ctx->m_invdiff.ensure((size_t)std::max(1, NE) * ctx->Mp * ctx->Mp));
+        CU(ctx->d_gcol_off.ensure(ctx->C + 1));
+        CU(cudaMemcpyAsync(ctx->d_gcol_off.p, ctx->gcol_off.data(), (ctx->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    }
     if (upload) {
         if (!pi || !T || !E) return fail(ctx, "estep: pi, T and E are required");
         if (!P) {
@@ -778,9 +833,9 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
             ctx->eig_store.resize((size_t)NE * (2 * (size_t)M * M + 2 * M + 1));
             double *eP = ctx->eig_store.data(), *ePi = eP + (size_t)NE * M * M, *ed = ePi + (size_t)NE * M * M,
                    *eds = ed + (size_t)NE * M, *esc = eds + (size_t)NE * M;
-            std::vector<int32_t> cplx(std::max(1, NE));
+            ctx->eig_cplx.assign(std::max(1, NE), 0);
             std::string msg;
-            if (smcb::host_eigensystems(M, K, NE, ctx->eig_keys.data(), T, E, eP, ePi, ed, eds, esc, cplx.data(), &msg))
+            if (smcb::host_eigensystems(M, K, NE, ctx->eig_keys.data(), T, E, eP, ePi, ed, eds, esc, ctx->eig_cplx.data(), &msg))
                 return fail(ctx, "estep: eigensystems: " + msg);
             P = eP; Pinv = ePi; d = ed; dsc = eds; scale = esc;
         } else if (n_eig != NE) {
@@ -802,7 +857,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         const double *di = ctx->d_in.p;
         launch_setup(ctx->model(), di + o_pi, di + o_T, di + o_E, di + o_P, di + o_Pi, di + o_d, di + o_ds, di + o_sc, ctx->st);
         ctx->stats.kernel_launches = 1;
-        launch_setup_pwtab(ctx->model(), ctx->st);
+        launch_setup_pwtab(ctx->model(), ctx->n_sm, ctx->st);
         ctx->stats.kernel_launches = 2;
         if (ctx->Mp == 32 || ctx->Mp == 64 || ctx->Mp == 128) { launch_setup_frags(ctx->model(), ctx->st); ctx->stats.kernel_launches = 3; }
     } else {
@@ -812,41 +867,72 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     const Model m = ctx->model();
     const Plan p = ctx->plan();
     const Work w = ctx->work();
-    // Drain the (tiny) setup work before the two recursion kernels are enqueued on their two streams: when the
-    // backward stream is parked on an event behind still-running setup kernels, the forward kernel takes the
-    // whole GPU first and the two passes run back to back instead of side by side (measured: 14.8 ms vs 8.1 ms).
-    if (upload) CU(cudaStreamSynchronize(ctx->st));
     cudaEventRecord(ctx->ev[1], ctx->st);
     CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
     CU(cudaMemsetAsync(w.fwd_rerun, 0, p.n_chunks, ctx->st));
-    cudaEventRecord(ctx->ev_setup_done, ctx->st);
-    // backward recursion runs concurrently on the second stream (it does not depend on alpha)
-    CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
-    cudaEventRecord(ctx->ev[5], ctx->st2);
     const bool mma = (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
     ctx->use_mma = mma;
-    if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
-    launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st2);
-    // forward recursion
-    if (mma && (ctx->opt_force_mma_forward || mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp))) launch_forward_mma(m, p, w, ctx->n_sm, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
+    const bool fwd_mma = mma && (ctx->opt_force_mma_forward || mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp, ctx->rec));
+    cudaEventRecord(ctx->ev[5], ctx->st);
+    if (fwd_mma && launch_recursions_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st)) {
+        // forward and backward recursion in one launch
+        ctx->stats.kernel_launches += 1;
+        cudaEventRecord(ctx->ev[6], ctx->st);
+        cudaEventRecord(ctx->ev[7], ctx->st);
+    } else {
+        // two launches on two streams: the backward recursion does not depend on alpha
+        cudaEventRecord(ctx->ev_setup_done, ctx->st);
+        CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
+        cudaEventRecord(ctx->ev[5], ctx->st2);
+        if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
+        cudaEventRecord(ctx->ev[6], ctx->st2);
+        if (fwd_mma) launch_forward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
+        cudaEventRecord(ctx->ev[7], ctx->st);
+        cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0));
+        ctx->stats.kernel_launches += 2;
+    }
+    launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st);
     launch_check_forward(m, p, w, (float)ctx->opt_fwd_tol0, (float)ctx->opt_fwd_tol, ctx->st);
-    ctx->stats.kernel_launches += 4;
-    cudaEventRecord(ctx->ev[7], ctx->st);
-    cudaEventRecord(ctx->ev[6], ctx->st2);
-    cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
-    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0));
+    ctx->stats.kernel_launches += 2;
+    enqueue_stats_and_finalize(ctx, m, p, w);
+    CU(cudaGetLastError());
+    ctx->stats.n_chunks = p.n_chunks;
+    ctx->stats.chunk_blocks = p.chunk_blocks;
+    ctx->stats.burn_in_blocks = p.burn_in;
+    ctx->stats.fwd_sweeps = ctx->stats.bwd_sweeps = 1;
+    ctx->stats.fwd_redone = ctx->stats.bwd_redone = 0;
+    ctx->stats.fwd_max_mismatch = ctx->stats.bwd_max_mismatch = 0.0;
+    ctx->stats.converged = 1;
+    ctx->pending = true;
+    return 0;
+}
+
+// Waits for the enqueued E-step; when a boundary check failed, runs the repair sweeps (Jacobi: every flagged chunk is
+// re-run from its neighbour's end value until the boundaries agree) and the statistics again.  `refetch` re-enqueues the
+// caller's device-to-host copies after a repair.
+template <typename F>
+static int complete_estep(smcpp_b200_ctx *ctx, F refetch)
+{
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    if (!ctx->pending) return 0;
+    ctx->pending = false;
+    const Model m = ctx->model();
+    const Plan p = ctx->plan();
+    const Work w = ctx->work();
     int fwd_sweeps = 1, bwd_sweeps = 1, fwd_redone = 0, bwd_redone = 0;
     float fwd_mm = 0.f, bwd_mm = 0.f;
+    bool repaired = false, gave_up = false;
     for (;;) {
-        CU(cudaMemcpyAsync(ctx->h_counters.p, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
         const int nf = ctx->h_counters.p[0], nb = ctx->h_counters.p[1];
         float f;
         std::memcpy(&f, &ctx->h_counters.p[2], 4); fwd_mm = std::max(fwd_mm, f);
         std::memcpy(&f, &ctx->h_counters.p[3], 4); bwd_mm = std::max(bwd_mm, f);
         if (ctx->h_counters.p[4] > 0) { ctx->stats.mma_rounds = ctx->h_counters.p[4]; ctx->stats.mma_steps = ctx->h_counters.p[5]; }
         if (nf == 0 && nb == 0) break;
-        if (fwd_sweeps + bwd_sweeps > ctx->opt_max_sweeps) break;
+        if (fwd_sweeps + bwd_sweeps > ctx->opt_max_sweeps) { gave_up = true; break; }
+        repaired = true;
         CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
         if (nf) {
             CU(cudaMemcpyAsync(w.end_alpha_prev, w.end_alpha, (size_t)p.n_chunks * m.Mp * sizeof(float),
@@ -866,6 +952,8 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
             bwd_redone += nb;
             ctx->stats.kernel_launches += 2;
         }
+        CU(cudaMemcpyAsync(ctx->h_counters.p, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
     }
     // a failed boundary check means the burn-in was too short for this model: lengthen it for the next E-step
     // (a near miss -- within 30x of the tolerance -- needs one notch: the recursions contract by ~1e-2 per 128 blocks on
@@ -881,48 +969,32 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
             ctx->burn_in_fwd_adapt += std::max(ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt, 256);
         }
     }
-    cudaEventRecord(ctx->ev[2], ctx->st);
-    launch_stats(m, p, w, ctx->st);
-    cudaEventRecord(ctx->ev[3], ctx->st);
-    ctx->gamma_valid = false;
-    if (ctx->save_gamma) {
-        // full posterior decoding (reference saveGamma, src/hmm.cpp:48-49,147-148): M x (L+1) doubles per contig
-        std::vector<int64_t> goff(ctx->C + 1, 0);
-        for (int c = 0; c < ctx->C; ++c) goff[c + 1] = goff[c] + (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
-        CU(ctx->w_gamma.ensure((size_t)goff[ctx->C] * M));
-        CU(ctx->m_invdiff.ensure((size_t)std::max(1, NE) * m.Mp * m.Mp));
-        CU(ctx->d_gcol_off.ensure(ctx->C + 1));
-        CU(cudaMemcpyAsync(ctx->d_gcol_off.p, goff.data(), (ctx->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));   // goff is a stack vector
-        launch_posterior(ctx->model(), p, w, ctx->w_gamma.p, ctx->d_gcol_off.p, ctx->st);
-        ctx->stats.kernel_launches += 2;
-        ctx->gamma_valid = true;
-    }
-    launch_finalize(m, p, w, ctx->st);
-    cudaEventRecord(ctx->ev[4], ctx->st);
-    // statistics: k_stats32 (+ k_stats32e when there are span>1 items) or the generic k_stats; finalize: 3 kernels
-    ctx->stats.kernel_launches += (((m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0) ? 2 : 1) + 3;
-    CU(cudaGetLastError());
-    ctx->stats.n_chunks = p.n_chunks;
-    ctx->stats.chunk_blocks = p.chunk_blocks;
-    ctx->stats.burn_in_blocks = p.burn_in;
     ctx->stats.fwd_sweeps = fwd_sweeps;
     ctx->stats.bwd_sweeps = bwd_sweeps;
     ctx->stats.fwd_redone = fwd_redone;
     ctx->stats.bwd_redone = bwd_redone;
     ctx->stats.fwd_max_mismatch = fwd_mm;
     ctx->stats.bwd_max_mismatch = bwd_mm;
+    if (gave_up) {
+        ctx->stats.converged = 0;
+        return fail(ctx, "estep: chunk boundaries still disagree after max_sweeps repair sweeps (results discarded); raise "
+                         "max_sweeps or burn_in_blocks");
+    }
+    if (repaired) {
+        enqueue_stats_and_finalize(ctx, m, p, w);
+        if (refetch()) return 1;
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
 static int finish_timing(smcpp_b200_ctx *ctx)
 {
-    CU(cudaStreamSynchronize(ctx->st));
-    CU(cudaGetLastError());
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.ms_setup = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_forward = ms;  // forward || backward + sweeps
-    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->stats.ms_backward = ms;   // backward pass 0 alone (second stream)
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_forward = ms;  // both recursions + checks (+ repair sweeps)
+    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->stats.ms_backward = ms;   // backward pass 0 alone when it is a launch of its own
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[7]); ctx->stats.ms_forward_only = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_stats = ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_finalize = ms;
@@ -983,26 +1055,32 @@ int smcpp_b200_host_emission(int npop, const int32_t *n, const int32_t *na, int 
     return rc;
 }
 
-int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)
+static int enqueue_fetch(smcpp_b200_ctx *ctx, bool ll, bool xisum, bool gamma0, bool gamma_sums, bool reduced)
 {
-    if (!ctx || !ctx->plan_valid) return 1;
-    CU(cudaSetDevice(ctx->device));
     const int C = ctx->C, M = ctx->M, K = ctx->K;
     double *h = ctx->h_out.p;
-    size_t o = 0;
     const size_t n_ll = C, n_x = (size_t)C * M * M, n_g0 = (size_t)C * M, n_gs = (size_t)C * K * M,
                  n_r = 1 + M + (size_t)M * M + (size_t)K * M;
-    double *h_ll = h + o; o += n_ll;
-    double *h_x = h + o; o += n_x;
-    double *h_g0 = h + o; o += n_g0;
-    double *h_gs = h + o; o += n_gs;
-    double *h_r = h + o;
+    double *h_ll = h, *h_x = h_ll + n_ll, *h_g0 = h_x + n_x, *h_gs = h_g0 + n_g0, *h_r = h_gs + n_gs;
     if (ll) CU(cudaMemcpyAsync(h_ll, ctx->o_ll.p, n_ll * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (xisum) CU(cudaMemcpyAsync(h_x, ctx->o_xisum.p, n_x * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (gamma0) CU(cudaMemcpyAsync(h_g0, ctx->o_gamma0.p, n_g0 * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (gamma_sums) CU(cudaMemcpyAsync(h_gs, ctx->o_gamma_sums.p, n_gs * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (reduced) CU(cudaMemcpyAsync(h_r, ctx->o_reduced.p, n_r * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)
+{
+    if (!ctx || !ctx->plan_valid) return 1;
+    DeviceGuard guard(ctx->device);
+    const int C = ctx->C, M = ctx->M, K = ctx->K;
+    const size_t n_ll = C, n_x = (size_t)C * M * M, n_g0 = (size_t)C * M, n_gs = (size_t)C * K * M,
+                 n_r = 1 + M + (size_t)M * M + (size_t)K * M;
+    auto fetch = [&]() { return enqueue_fetch(ctx, ll != nullptr, xisum != nullptr, gamma0 != nullptr, gamma_sums != nullptr, reduced != nullptr); };
+    if (fetch()) return 1;
+    if (complete_estep(ctx, fetch)) return 1;     // one synchronisation; repairs + copies again if a boundary check failed
+    const double *h_ll = ctx->h_out.p, *h_x = h_ll + n_ll, *h_g0 = h_x + n_x, *h_gs = h_g0 + n_g0, *h_r = h_gs + n_gs;
     if (ll) std::memcpy(ll, h_ll, n_ll * 8);
     if (xisum) std::memcpy(xisum, h_x, n_x * 8);
     if (gamma0) std::memcpy(gamma0, h_g0, n_g0 * 8);
@@ -1016,6 +1094,7 @@ int smcpp_b200_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
                      double *ll, double *xisum, double *gamma0, double *gamma_sums, double *reduced)
 {
     if (!ctx) return 1;
+    DeviceGuard guard(ctx->device);
     if (run_estep(ctx, M, pi, T, E, n_eig, P, Pinv, d, d_scaled, scale, true)) return 1;
     if (smcpp_b200_fetch(ctx, ll, xisum, gamma0, gamma_sums, reduced)) return 1;
     return finish_timing(ctx);
@@ -1026,8 +1105,10 @@ int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const 
                             const double *scale, int upload_inputs)
 {
     if (!ctx) return 1;
+    DeviceGuard guard(ctx->device);
     if (!upload_inputs && (!ctx->plan_valid || ctx->M != M)) return fail(ctx, "estep_device: no resident inputs for this M");
     if (run_estep(ctx, M, pi, T, E, n_eig, P, Pinv, d, d_scaled, scale, upload_inputs != 0)) return 1;
+    if (complete_estep(ctx, []() { return 0; })) return 1;
     return finish_timing(ctx);
 }
 
@@ -1044,7 +1125,7 @@ int smcpp_b200_copy_reduced_to_device(smcpp_b200_ctx *ctx, void *dst_device, int
     if (!ctx || !ctx->plan_valid || !dst_device) return 1;
     const int64_t n = 1 + ctx->M + (int64_t)ctx->M * ctx->M + (int64_t)ctx->K * ctx->M;
     if (count != n) return fail(ctx, "copy_reduced_to_device: count mismatch");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     CU(cudaMemcpyAsync(dst_device, ctx->o_reduced.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return 0;
@@ -1061,7 +1142,7 @@ int smcpp_b200_fetch_gamma(smcpp_b200_ctx *ctx, int contig, double *out)
 {
     if (!ctx || !out || contig < 0 || contig >= ctx->C) return 1;
     if (!ctx->gamma_valid) return fail(ctx, "fetch_gamma: the last estep() ran without save_gamma");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     int64_t off = 0;
     for (int c = 0; c < contig; ++c) off += (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
     const int64_t cols = (ctx->blk_off[contig + 1] - ctx->blk_off[contig]) + 1;
@@ -1080,20 +1161,20 @@ int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out)
 int smcpp_b200_fp64_peak(smcpp_b200_ctx *ctx, double *tflops)
 {
     if (!ctx || !tflops) return 1;
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     CU(ctx->w_counters.ensure(8));
     double *sink = reinterpret_cast<double *>(ctx->w_counters.p);
     const int iters = 1 << 14;
-    launch_fp64_peak(sink, 256, ctx->st);  // warm-up
+    launch_fp64_peak(sink, 256, ctx->n_sm, ctx->st);  // warm-up
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(ctx->ev[5], ctx->st);
-        launch_fp64_peak(sink, iters, ctx->st);
+        launch_fp64_peak(sink, iters, ctx->n_sm, ctx->st);
         cudaEventRecord(ctx->ev[6], ctx->st);
         CU(cudaStreamSynchronize(ctx->st));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
-        const double flop = 2.0 * 8.0 * iters * 256.0 * 148.0 * 8.0;
+        const double flop = 2.0 * 8.0 * iters * 256.0 * (double)ctx->n_sm * 8.0;
         best = std::max(best, flop / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
@@ -1110,12 +1191,12 @@ int smcpp_b200_stream(smcpp_b200_ctx *ctx, void **stream)
 int smcpp_b200_debug_alpha_hat(smcpp_b200_ctx *ctx, int contig, float *out)
 {
     if (!ctx || !ctx->plan_valid || contig < 0 || contig >= ctx->C || !out) return 1;
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const int64_t L = ctx->blk_off[contig + 1] - ctx->blk_off[contig];
     const size_t n = (size_t)(L + 1) * ctx->M;
     float *dbuf = nullptr;
     CU(cudaMalloc(&dbuf, n * sizeof(float)));
-    launch_gather_alpha(ctx->model(), ctx->plan(), ctx->work(), contig, dbuf, ctx->st);
+    launch_gather_alpha(ctx->model(), ctx->plan(), ctx->work(), contig, dbuf, ctx->n_sm, ctx->st);
     cudaError_t e = cudaMemcpyAsync(out, dbuf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
     cudaFree(dbuf);

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
     for (int b = b0; b < bend; ++b) {
         const int span = p.span[g0 + b];
         const int kc = p.kcode[g0 + b];
-        const int k = kc & 2047, e = (kc >> 11) - 1;
+        const int k = kc & kKeyMask, e = (kc >> kKeyBits) - 1;
         double logc;
         float sf = 0.f;
         if (e >= 0) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
         const bool storing = b < bend;
         const int span = p.span[g0 + b];
         const int kc = p.kcode[g0 + b];
-        const int k = kc & 2047, e = (kc >> 11) - 1;
+        const int k = kc & kKeyMask, e = (kc >> kKeyBits) - 1;
         double *bv = w.bvec + (size_t)(g0 + b) * Mp;
         double nb[R];
 #pragma unroll
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
     const int NB = stats_tile_blocks(Mp);
     const int slab = blockIdx.x;
     const int t = p.sl_contig[slab], s0 = p.sl_start[slab], n = p.sl_len[slab];
-    const uint32_t mask = p.sl_mask[slab];
+    const uint32_t *mask = p.sl_mask + (size_t)slab * p.mask_words;
     const int64_t g0 = p.blk_off[t];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ty = tid >> 4, tx = tid & 15;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
     };
 
     // ---------------- span-1 blocks
-    if (mask & 1u) {
+    if (mask_bit(mask, 0)) {
         double acc[TM][TM];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -463,9 +463,9 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
             for (int bq = warp; bq < NB; bq += NW) {
                 const int b = s0 + tile0 + bq;
                 int valid = 0, k = 0;
-                if (tile0 + bq < n && (p.kcode[g0 + b] >> 11) == 0) {
+                if (tile0 + bq < n && (p.kcode[g0 + b] >> kKeyBits) == 0) {
                     valid = 1;
-                    k = p.kcode[g0 + b] & 2047;
+                    k = p.kcode[g0 + b] & kKeyMask;
                     const float *ap = alpha_col(b), *ac = ap + Mp;
                     const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
                     double be[R], acur[R], part = 0.0;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 
     // ---------------- span>1 blocks, one pass per eigen key present in the slab
     for (int e = 0; e < m.n_eig; ++e) {
-        if (!(mask & (2u << e))) continue;
+        if (!mask_bit(mask, 1 + e)) continue;
         double acc[TM][TM];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
                 int valid = 0;
                 if (tile0 + bq < n) {
                     const int span = p.span[g0 + b];
-                    if ((p.kcode[g0 + b] >> 11) == e + 1) {
+                    if ((p.kcode[g0 + b] >> kKeyBits) == e + 1) {
                         valid = 1;
                         const float *ap = alpha_col(b);
                         const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
@@ -654,11 +654,11 @@ __global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w
     const int sl0 = p.slab_off[t], sl1 = p.slab_off[t + 1];
     const double *src;
     size_t sstride;
-    uint32_t bit;
-    if (x < oR) { src = w.Xpart + x; sstride = MM; bit = 1u; }
-    else if (x < oD) { const size_t y = x - oR; src = w.Rpart + y; sstride = (size_t)NE * MM; bit = 2u << (int)(y / MM); }
-    else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 2u << (int)(y / Mp); }
-    else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 1u; }
+    int bit;
+    if (x < oR) { src = w.Xpart + x; sstride = MM; bit = 0; }
+    else if (x < oD) { const size_t y = x - oR; src = w.Rpart + y; sstride = (size_t)NE * MM; bit = 1 + (int)(y / MM); }
+    else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 1 + (int)(y / Mp); }
+    else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 0; }
     double acc = 0.0;
     if ((Mp == 32 || Mp == 64 || Mp == 128) && x >= oR && x < oG) {
         // M <= 64: R_e / D_e partials come per work item of k_stats32e / k_stats64e (fixed order: bitwise reproducible)
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w
         }
     } else {
         for (int s = sl0; s < sl1; ++s)
-            if (p.sl_mask[s] & bit) acc += src[(size_t)s * sstride];
+            if (mask_bit(p.sl_mask + (size_t)s * p.mask_words, bit)) acc += src[(size_t)s * sstride];
     }
     w.sums[(size_t)t * stride + x] = acc;
 }
@@ -681,20 +681,12 @@ __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
 {
     const int M = m.M, Mp = m.Mp, K = m.K, NE = m.n_eig;
     const int t = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-    const int sl0 = p.slab_off[t], sl1 = p.slab_off[t + 1];
     const size_t MM = (size_t)Mp * Mp;
     const size_t oR = MM, oD = oR + (size_t)NE * MM, oG = oD + (size_t)NE * Mp, stride = oG + (size_t)K * Mp;
     double *S = w.sums + (size_t)t * stride;
     double *X = S;                                     // accumulates in place
     double *A = w.scratch + (size_t)t * 2 * MM, *G = A + MM;
-    __shared__ uint32_t cmask;
-    if (tid == 0) {
-        uint32_t mk = 0;
-        for (int s = sl0; s < sl1; ++s) mk |= p.sl_mask[s];
-        cmask = mk;
-    }
-    __syncthreads();
-    const uint32_t mask = cmask;
+    const uint32_t *mask = p.ct_mask + (size_t)t * p.mask_words;   // which eigen keys occur in this contig
     double *gso = w.gamma_sums + (size_t)t * K * M;
     for (int x = tid; x < K * M; x += nth) {
         const int k = x / M, j = x % M;
@@ -702,7 +694,7 @@ __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
     }
     __syncthreads();
     for (int e = 0; e < NE; ++e) {
-        if (!(mask & (2u << e))) continue;
+        if (!mask_bit(mask, 1 + e)) continue;
         const double *dsc = m.dsc + (size_t)e * Mp, *dr = m.dr + (size_t)e * Mp;
         const double *P = m.P + (size_t)e * Mp * Mp, *Pinv = m.Pinv + (size_t)e * Mp * Mp;
         const double *R = S + oR + (size_t)e * MM, *D = S + oD + (size_t)e * Mp;
@@ -806,12 +798,12 @@ __global__ void k_setup_pwtab(Model m)
     }
 }
 
-void launch_setup_pwtab(const Model &m, cudaStream_t st)
+void launch_setup_pwtab(const Model &m, int n_sm, cudaStream_t st)
 {
     const long n = (long)m.n_eig * m.n_span * m.Mp;
     if (n <= 0) return;
     int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > n_sm * 16) blocks = n_sm * 16;
     k_setup_pwtab<<<blocks, 256, 0, st>>>(m);
 }
 
@@ -834,9 +826,9 @@ __global__ void k_gather_alpha(Model m, Plan p, Work w, int t, float *out)
     }
 }
 
-void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st)
+void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st)
 {
-    k_gather_alpha<<<592, 256, 0, st>>>(m, p, w, contig, out);
+    k_gather_alpha<<<n_sm * 4, 256, 0, st>>>(m, p, w, contig, out);
 }
 
 // FP64 FMA peak probe: 8 independent chains per thread, 8 warps x 8 CTAs per SM
@@ -852,6 +844,6 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *sink, int iters)
     if (r == 123.456) sink[0] = r;
 }
 
-void launch_fp64_peak(double *sink, int iters, cudaStream_t st) { k_fp64_peak<<<148 * 8, 256, 0, st>>>(sink, iters); }
+void launch_fp64_peak(double *sink, int iters, int n_sm, cudaStream_t st) { k_fp64_peak<<<n_sm * 8, 256, 0, st>>>(sink, iters); }
 
 }  // namespace smcb

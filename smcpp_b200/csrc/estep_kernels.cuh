@@ -15,7 +15,11 @@
 namespace smcb {
 
 constexpr int kMaxMp = 128;       // padded state count limit (M <= 128)
-constexpr int kMaxEig = 30;       // eigen keys representable in a slab type mask
+// per-block code (Plan::kcode): bits 0-15 key id, bits 16-31 1 + eigen index if span > 1 (else 0)
+typedef uint32_t kcode_t;
+constexpr int kKeyBits = 16;
+constexpr int kKeyMask = 0xffff;
+constexpr int kMaxKeys = 65535;   // distinct observation keys; also bounds the keys that occur with span > 1
 
 // Per-E-step operands on the device.  All matrices are padded to Mp = 32*ceil(M/32) in the fast
 // (lane) dimension; pads are zero.
@@ -66,7 +70,7 @@ struct Plan {
     int64_t total_blocks;
     // per block (concatenated over contigs)
     const int32_t *span;     // [total]
-    const uint16_t *kcode;   // [total]  bits 0-10: key id; bits 11-15: 1 + eigen index if span > 1, else 0
+    const kcode_t *kcode;    // [total]  bits 0-15: key id; bits 16-31: 1 + eigen index if span > 1, else 0
     const int32_t *span_id;  // [total]  index into Model::span_list (0 for span-1 blocks)
     // per contig
     const int64_t *blk_off;  // [C+1] first global block of contig
@@ -81,7 +85,9 @@ struct Plan {
     const int32_t *sl_contig;// [n_slabs]
     const int32_t *sl_start; // [n_slabs]
     const int32_t *sl_len;   // [n_slabs]
-    const uint32_t *sl_mask; // [n_slabs] bit0: has span-1 blocks; bit 1+e: has span>1 blocks of eigen key e
+    const uint32_t *sl_mask; // [n_slabs][mask_words] bit set: bit 0 = has span-1 blocks; bit 1+e = has span>1 blocks of eigen key e
+    const uint32_t *ct_mask; // [n_contigs][mask_words] the same per contig (union over its slabs)
+    int mask_words;          // ceil((1 + n_eig) / 32)
     // processing order of the statistics kernel: per slab [span-1 blocks sorted by key | eigen key 0 | eigen key 1 ...]
     const int2 *srec;        // [total]  (block index within the contig, key id for span-1 blocks / span id otherwise), at the slab's own offset
     const int32_t *seg;      // [n_slabs][n_eig + 2] segment boundaries (relative to the slab start)
@@ -96,6 +102,8 @@ struct Plan {
     const int32_t *it_eig;   // [n_items]
     const int32_t *it_off;   // [C * n_eig + 1] first item of (contig, eigen key)
 };
+
+__host__ __device__ inline bool mask_bit(const uint32_t *mask, int bit) { return (mask[bit >> 5] >> (bit & 31)) & 1u; }
 
 // Work buffers.
 struct Work {
@@ -141,22 +149,27 @@ int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
 void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 64
 constexpr int kItemBlocks = 4096;   // span>1 blocks per work item of k_stats32e
-void launch_setup_pwtab(const Model &m, cudaStream_t st);
+void launch_setup_pwtab(const Model &m, int n_sm, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
-void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);   // Mp in {32, 64, 128}, pass 0, <= 8 chunks / warp
-void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st);
-int resident_warps_mma(int n_sm, int Mp);
-void set_fwd_cached_keys(int n);
-void set_chunks_per_warp(int g);
-bool mma_forward_pays(int n_chunks, int n_sm, int Mp);
+struct RecOpts {             // per-context tuning of the tensor-path recursions (set_option)
+    int cached_keys = 0;     // span-1 keys whose float step matrix is resident in shared memory (M <= 32), 0..4 (measured: no gain, the
+                             // LSU data pipe carries the same bytes into the registers either way)
+    int force_G = 0;         // chunks per warp pinned to 1 / 2 / 4 / 8 (0 = automatic)
+    int fused = 1;           // forward and backward recursion in one launch (k_recursions_mma)
+};
+bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);
+void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);   // Mp in {32, 64, 128}, pass 0, <= 8 chunks / warp
+void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);
+int resident_warps_mma(int n_sm, int Mp, const RecOpts &o);
+bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
-void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, cudaStream_t st);
-void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, cudaStream_t st);
+void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st);
+void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
-void launch_fp64_peak(double *sink, int iters, cudaStream_t st);
+void launch_fp64_peak(double *sink, int iters, int n_sm, cudaStream_t st);
 
 }  // namespace smcb

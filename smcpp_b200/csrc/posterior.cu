@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, 
         const float *ap = w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (b - cb * Lc)) * Mp;   // alpha_{l-1}; alpha_l = ap + Mp
         const double *bv = w.bvec + (size_t)(g0 + b) * Mp;
         const int kc = p.kcode[g0 + b];
-        const int e = (kc >> 11) - 1;
+        const int e = (kc >> kKeyBits) - 1;
         if (e < 0) {
             double v[R], part = 0.0;
 #pragma unroll
@@ -149,14 +149,14 @@ __global__ void k_setup_invdiff(Model m)
     }
 }
 
-void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, cudaStream_t st)
+void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st)
 {
     {
         const long n = (long)m.n_eig * m.Mp * m.Mp;
         if (n > 0) k_setup_invdiff<<<(int)((n + 255) / 256), 256, 0, st>>>(m);
     }
     const size_t smem = (size_t)kPostWarps * 5 * m.Mp * sizeof(double);
-    const int blocks = 148 * 8;
+    const int blocks = n_sm * 8;
     switch (m.Mp / 32) {
     case 1: k_posterior<1><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;
     case 2: k_posterior<2><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;

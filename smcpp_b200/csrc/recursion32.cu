@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_forward32(Model m, Plan p, Wo
     }
     {
         const int sp0 = __shfl_sync(kFull, sp_n, 0), kc0 = __shfl_sync(kFull, kc_n, 0);
-        if ((kc0 >> 11) - 1 == hot && hot >= 0) pw_hot = pow_span(dsc_h, logd_h, sp0);
+        if ((kc0 >> kKeyBits) - 1 == hot && hot >= 0) pw_hot = pow_span(dsc_h, logd_h, sp0);
     }
     for (int base = b0; base < bend; base += 32) {
         const int sp_l = sp_n, kc_l = kc_n;
@@ -125,13 +125,13 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_forward32(Model m, Plan p, Wo
             const int b = base + tt;
             const int span = __shfl_sync(kFull, sp_l, tt);
             const int kc = __shfl_sync(kFull, kc_l, tt);
-            const int k = kc & 2047, e = (kc >> 11) - 1;
+            const int k = kc & kKeyMask, e = (kc >> kKeyBits) - 1;
             // d~^span of the NEXT step (independent of this step's dependency chain)
             double pw_next = 1.0;
             {
                 const int spx = tt + 1 < 32 ? __shfl_sync(kFull, sp_l, (tt + 1) & 31) : __shfl_sync(kFull, sp_n, 0);
                 const int kcx = tt + 1 < 32 ? __shfl_sync(kFull, kc_l, (tt + 1) & 31) : __shfl_sync(kFull, kc_n, 0);
-                if (hot >= 0 && (kcx >> 11) - 1 == hot) pw_next = pow_span(dsc_h, logd_h, spx);
+                if (hot >= 0 && (kcx >> kKeyBits) - 1 == hot) pw_next = pow_span(dsc_h, logd_h, spx);
             }
             double cmul, cadd = 0.0;    // this step's normaliser = cmul * exp(cadd)
             float sf = 0.f;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_backward32(Model m, Plan p, W
     double pw_hot = 1.0;
     {
         const int sp0 = __shfl_sync(kFull, sp_n, 0), kc0 = __shfl_sync(kFull, kc_n, 0);
-        if ((kc0 >> 11) - 1 == hot && hot >= 0) pw_hot = pow_span(dsc_h, logd_h, sp0);
+        if ((kc0 >> kKeyBits) - 1 == hot && hot >= 0) pw_hot = pow_span(dsc_h, logd_h, sp0);
     }
     int since = 0;
     for (int top = b1 - 1; top >= s; top -= 32) {
@@ -283,12 +283,12 @@ __global__ void __launch_bounds__(kWarps32 * 32) k_backward32(Model m, Plan p, W
             const bool storing = b < bend;
             const int span = __shfl_sync(kFull, sp_l, tt);
             const int kc = __shfl_sync(kFull, kc_l, tt);
-            const int k = kc & 2047, e = (kc >> 11) - 1;
+            const int k = kc & kKeyMask, e = (kc >> kKeyBits) - 1;
             double pw_next = 1.0;
             {
                 const int spx = tt + 1 < 32 ? __shfl_sync(kFull, sp_l, (tt + 1) & 31) : __shfl_sync(kFull, sp_n, 0);
                 const int kcx = tt + 1 < 32 ? __shfl_sync(kFull, kc_l, (tt + 1) & 31) : __shfl_sync(kFull, kc_n, 0);
-                if (hot >= 0 && (kcx >> 11) - 1 == hot) pw_next = pow_span(dsc_h, logd_h, spx);
+                if (hot >= 0 && (kcx >> kKeyBits) - 1 == hot) pw_next = pow_span(dsc_h, logd_h, spx);
             }
             double *bv = w.bvec + (size_t)(g0 + b) * 32;
             double nb;

@@ -128,10 +128,18 @@ __device__ __forceinline__ void lds2p(const float *p, f32x2 &a, f32x2 &b)   // 1
 
 // y[j] = fl(y[j] + fl(x_i A(i, j))) for i = 0..MP-1 in order, for this lane's 8 NS columns (packed in pairs):
 // the reference's k-sequential axpy order with the float-rounded step matrix (src/hmm.cpp:85-89).
-// A points at this lane's columns of row 0 (row stride 4 NI floats), in global memory (read-only path) or, for the
-// frequent span-1 keys, in shared memory (kSm): ncu r1g showed the global variant parked on the long scoreboard for
-// ~200 cycles per 4 rows -- the step matrices of 60+ keys do not stay in L1 next to the streaming alpha / beta traffic.
-template <int NS, bool kSm>
+// A points at this lane's columns of row 0 (row stride 4 NI floats).  MODE says where the matrix lives:
+//   kAGlobal   global memory through the read-only path (one 256-bit load per row part)
+//   kAShared   shared memory (every chunk of the warp has one of the resident keys)
+//   kAGeneric  per lane either of the two (generic 128-bit loads): the frequent keys' matrices are resident in shared
+//              memory, the rare ones (60+ full-SFS keys, 4 KB each) come through L1 / L2
+// ncu r2a: with all matrices in global memory the L1 hit rate is 54 % and 30 % of the kernel's samples wait on these loads.
+constexpr int kAGlobal = 0, kAShared = 1, kAGeneric = 2;
+__device__ __forceinline__ void ldgen2p(const float *p, f32x2 &a, f32x2 &b)   // 128-bit generic load of 4 floats as 2 packed pairs
+{
+    asm("ld.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+template <int NS, int MODE>
 __device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32x2 (&y2)[4 * NS], f32x2 kNegZero2, f32x2 kOne2)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS;
@@ -146,8 +154,9 @@ __device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32
 #pragma unroll
             for (int h = 0; h < NS; ++h) {
                 f32x2x4 av;
-                if (kSm) { lds2p(Ai + 8 * h, av.v[0], av.v[1]); lds2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
-                else av = ldg256p(Ai + 8 * h);   // (two 128-bit loads raise the L1 hit rate 55 -> 70 % but not the speed: the LSU return path is the limit)
+                if (MODE == kAShared) { lds2p(Ai + 8 * h, av.v[0], av.v[1]); lds2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
+                else if (MODE == kAGeneric) { ldgen2p(Ai + 8 * h, av.v[0], av.v[1]); ldgen2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
+                else av = ldg256p(Ai + 8 * h);
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2)   // two columns per instruction
                     y2[4 * h + j2] = fma2(fma2(xx, av.v[j2], kNegZero2), kOne2, y2[4 * h + j2]);
@@ -219,9 +228,9 @@ __device__ __forceinline__ void ldg_if(int &dst, const int32_t *ptr, bool pred)
 {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.b32 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
 }
-__device__ __forceinline__ void ldg_if(int &dst, const uint16_t *ptr, bool pred)
+__device__ __forceinline__ void ldg_if(int &dst, const kcode_t *ptr, bool pred)
 {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.u16 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.b32 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
 }
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
@@ -235,7 +244,7 @@ struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of t
 // forward and backward then run one after the other), shared memory (all warps of both kernels resident at once) or
 // global memory through the read-only path (M = 128: a fragment table is 128 KB).  The launcher picks.
 template <int NS, int FRAG>
-__global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G, int nkc)
+__device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int nkc, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP, XS = MP + 4;
     constexpr int NF = FRAG == kFragReg ? 32 : 1;
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
     const int M = m.M;
 
     // G (<= 8) chunks per warp: small inputs spread over more warps (rows n >= G of the MMA stay idle)
-    const int c = n < G ? (blockIdx.x * kMW + warp) * G + n : p.n_chunks;
+    const int c = n < G ? (bid * kMW + warp) * G + n : p.n_chunks;
     bool active = c < p.n_chunks;
     const int cc = active ? c : 0;
     const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
@@ -327,23 +336,23 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) pwv[nt] = make_double2(0.0, 0.0);
     auto load_pw = [&]() {   // states st(q, 2nt), st(q, 2nt + 1) of the q-major table
-        const double2 *pw = reinterpret_cast<const double2 *>(m.pwq + ((size_t)((kc >> 11) - 1) * m.n_span + sid) * MP + q * NI);
+        const double2 *pw = reinterpret_cast<const double2 *>(m.pwq + ((size_t)((kc >> kKeyBits) - 1) * m.n_span + sid) * MP + q * NI);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + nt);
     };
     fetch_cur();
-    if (active && (kc >> 11) > 0) load_pw();
+    if (active && (kc >> kKeyBits) > 0) load_pw();
 
     for (;;) {
         const unsigned am = __ballot_sync(kAll, active);
         if (!am) break;
         ++rounds;
-        const int type = active ? (kc >> 11) : -1;
+        const int type = active ? (kc >> kKeyBits) : -1;
         // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
         const int T = __shfl_sync(kAll, type, lead & 31);
         const bool adv = active && type == T;
-        const int k = adv ? (kc & 2047) : (nkc > 0 ? m.hot_keys[0] : 0);
+        const int k = adv ? (kc & kKeyMask) : (nkc > 0 ? m.hot_keys[0] : 0);
         float xn[NI];
         double cmul = 1.0, cadd = 0.0;
         float sf = 0.f;
@@ -390,11 +399,14 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             int slot = -1;
             for (int sl = 0; sl < nkc; ++sl)
                 if (k == m.hot_keys[sl]) slot = sl;
-            if (nkc > 0 && __all_sync(kAll, slot >= 0)) {
-                float_gemv<NS, true>(s_A + (size_t)slot * MM + q * NI, xr, y2, m.c_negzero2, m.c_one2);
+            // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
+            const float *Ag = m.A32q + ((size_t)k * MP * 4 + q) * NI;
+            if (nkc == 0) {
+                float_gemv<NS, kAGlobal>(Ag, xr, y2, m.c_negzero2, m.c_one2);
+            } else if (__all_sync(kAll, slot >= 0)) {
+                float_gemv<NS, kAShared>(s_A + (size_t)slot * MM + q * NI, xr, y2, m.c_negzero2, m.c_one2);
             } else {
-                // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
-                float_gemv<NS, false>(m.A32q + ((size_t)k * MP * 4 + q) * NI, xr, y2, m.c_negzero2, m.c_one2);
+                float_gemv<NS, kAGeneric>(slot >= 0 ? s_A + (size_t)slot * MM + q * NI : Ag, xr, y2, m.c_negzero2, m.c_one2);
             }
             float y[NI];
 #pragma unroll
@@ -453,15 +465,17 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
             ldg_if(obn.sp_hi, p.span + i1, rot); ldg_if(obn.kc_hi, p.kcode + i1, rot); ldg_if(obn.id_hi, p.span_id + i1, rot);
         }
         fetch_cur();
-        if (adv && active && (kc >> 11) > 0) load_pw();
+        if (adv && active && (kc >> kKeyBits) > 0) load_pw();
         if constexpr (NS == 1) {
             // float step matrix of the block AFTER the next one -> L1 (one full round ahead).  The matrices of the rare keys
             // (60+ full-SFS keys, 4 KB each) do not stay in L1; without this every 4-row group of their GEMV waits on L2.
             const int pos2 = cur + 1 - base;
             const int v2 = pos2 < 8 ? ((pos2 & 4) ? ob.kc_hi : ob.kc_lo) : obn.kc_lo;
             const int kc2 = __shfl_sync(kAll, v2, (lane & ~3) | (pos2 & 3));
-            if (adv && active && cur + 1 < bend && (kc2 >> 11) == 0 && (kc2 & 2047) != m.hot_keys[0]) {
-                const float *row = m.A32q + ((size_t)(kc2 & 2047) * MP + 8 * q) * 4 * NI;   // rows 8q .. 8q + 7, 128 B each
+            bool resident = (kc2 & kKeyMask) == m.hot_keys[0];
+            for (int sl = 1; sl < nkc; ++sl) resident = resident || (kc2 & kKeyMask) == m.hot_keys[sl];
+            if (adv && active && cur + 1 < bend && (kc2 >> kKeyBits) == 0 && !resident) {
+                const float *row = m.A32q + ((size_t)(kc2 & kKeyMask) * MP + 8 * q) * 4 * NI;   // rows 8q .. 8q + 7, 128 B each
 #pragma unroll
                 for (int j = 0; j < 8; ++j) prefetch_l1(row + (size_t)j * 4 * NI);
             }
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work 
 
 // =============================================== backward ==================================================
 template <int NS, int FRAG>
-__global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work w, int G)
+__device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP;
     constexpr int NF = FRAG == kFragReg ? 32 : 1;
@@ -509,7 +523,7 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
     __syncthreads();
     const int M = m.M;
 
-    const int c = n < G ? (blockIdx.x * kMW + (tid >> 5)) * G + n : p.n_chunks;
+    const int c = n < G ? (bid * kMW + (tid >> 5)) * G + n : p.n_chunks;
     bool active = c < p.n_chunks;
     const int cc = active ? c : 0;
     const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
@@ -554,8 +568,8 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) opv[nt] = make_double2(0.0, 0.0);
     auto load_op = [&]() {
-        const int ty = kc >> 11;
-        const double *row = ty > 0 ? m.pwq + ((size_t)(ty - 1) * m.n_span + sid) * MP : m.Eq + (size_t)(kc & 2047) * MP;
+        const int ty = kc >> kKeyBits;
+        const double *row = ty > 0 ? m.pwq + ((size_t)(ty - 1) * m.n_span + sid) * MP : m.Eq + (size_t)(kc & kKeyMask) * MP;
         const double2 *src = reinterpret_cast<const double2 *>(row + q * NI);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) opv[nt] = __ldg(src + nt);
@@ -566,7 +580,7 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
     for (;;) {
         const unsigned am = __ballot_sync(kAll, active);
         if (!am) break;
-        const int type = active ? (kc >> 11) : -1;
+        const int type = active ? (kc >> kKeyBits) : -1;
         const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
         const int T = __shfl_sync(kAll, type, lead & 31);
         const bool adv = active && type == T;
@@ -658,22 +672,57 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
     }
 }
 
+template <int NS, int FRAG>
+__global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G, int nkc)
+{
+    forward_mma_body<NS, FRAG>(m, p, w, G, nkc, blockIdx.x);
+}
+
+template <int NS, int FRAG>
+__global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work w, int G)
+{
+    backward_mma_body<NS, FRAG>(m, p, w, G, blockIdx.x);
+}
+
+// Both recursions in ONE launch: the forward and the backward pass are independent (the statistics need both), and they
+// complement each other on an SM -- the forward pass spends half of its rounds on the FP32 pipe (float step), the backward
+// pass lives on the FP64 tensor pipe.  A CTA is either a forward or a backward CTA.  CTAs are handed to the SMs in
+// layers of n_sm consecutive block indices, so the role alternates with the block index AND flips from layer to layer:
+// every SM gets the same number of CTAs of each role (with `role = bid & 1` an even SM count would give half of the
+// SMs forward CTAs only).  This replaces two streams + an event + a host synchronisation between setup and recursions
+// (two kernels enqueued behind running setup kernels started one after the other instead of side by side).
+template <int NS, int FRAG>
+__global__ void __launch_bounds__(kMW * 32) k_recursions_mma(Model m, Plan p, Work w, int G, int nkc, int blocks, int layer)
+{
+    const int bid = blockIdx.x;
+    int role, idx;
+    if (layer > 0) {
+        const int L = bid / layer, pos = bid - L * layer;
+        role = (pos + L) & 1;
+        idx = L * (layer >> 1) + (pos >> 1);
+    } else {
+        role = bid & 1;
+        idx = bid >> 1;
+    }
+    if (idx >= blocks) return;
+    if (role == 0) forward_mma_body<NS, FRAG>(m, p, w, G, nkc, idx);
+    else backward_mma_body<NS, FRAG>(m, p, w, G, idx);
+}
+
 // ---- launch -------------------------------------------------------------------------------------------------
-// number of span-1 keys whose float step matrix the forward kernel keeps in shared memory (M <= 32 only; option
-// "fwd_cached_keys"): 4 KB each
-static int g_cached_keys = 0;   // measured on C3: 0 -> 7.88 ms, 4 -> 8.12 ms for the recursion phase (L1 capacity matters more)
-void set_fwd_cached_keys(int n) { g_cached_keys = n < 0 ? 0 : (n > 4 ? 4 : n); }
-static int cached_keys(const Model &m)
+// RecOpts::cached_keys: number of span-1 keys whose float step matrix the forward kernel keeps in shared memory
+// (M <= 32 only; option "fwd_cached_keys"), 4 KB each.  Lanes whose key is resident read shared memory, the others the
+// read-only path (float_gemv<kAGeneric>).
+static int cached_keys(const Model &m, const RecOpts &o)
 {
     if (m.Mp != 32) return 0;
     int n = 0;
-    while (n < g_cached_keys && n < 4 && m.hot_keys[n] >= 0) ++n;
+    while (n < o.cached_keys && n < 4 && m.hot_keys[n] >= 0) ++n;
     return n;
 }
-static size_t fwd_smem(int NS, int frag, int nkc = -1)
+static size_t fwd_smem(int NS, int frag, int nkc)
 {
     const size_t MP = 32 * NS;
-    if (nkc < 0) nkc = NS == 1 ? g_cached_keys : 0;
     return (frag == kFragShared ? 2 * MP * MP * sizeof(double) : 0) + (size_t)kMW * 8 * (MP + 4) * sizeof(float) +
            (size_t)nkc * MP * MP * sizeof(float);
 }
@@ -683,17 +732,18 @@ static size_t bwd_smem(int NS, int frag)
     return frag == kFragGlobal ? 16 : (frag == kFragShared ? 3 : 1) * MP * MP * sizeof(double);
 }
 
-int resident_warps_mma(int n_sm, int Mp)
+int resident_warps_mma(int n_sm, int Mp, const RecOpts &o)
 {
     int bf = 0, bb = 0;
     if (Mp == 32) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<1, kFragShared>, kMW * 32, fwd_smem(1, kFragShared));
+        const int nkc = o.cached_keys < 0 ? 0 : (o.cached_keys > 4 ? 4 : o.cached_keys);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<1, kFragShared>, kMW * 32, fwd_smem(1, kFragShared, nkc));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<1, kFragShared>, kMW * 32, bwd_smem(1, kFragShared));
     } else if (Mp == 64) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<2, kFragShared>, kMW * 32, fwd_smem(2, kFragShared));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<2, kFragShared>, kMW * 32, fwd_smem(2, kFragShared, 0));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<2, kFragShared>, kMW * 32, bwd_smem(2, kFragShared));
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<4, kFragGlobal>, kMW * 32, fwd_smem(4, kFragGlobal));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<4, kFragGlobal>, kMW * 32, fwd_smem(4, kFragGlobal, 0));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<4, kFragGlobal>, kMW * 32, bwd_smem(4, kFragGlobal));
     }
     int b = bf < bb ? bf : bb;
@@ -702,11 +752,10 @@ int resident_warps_mma(int n_sm, int Mp)
 }
 
 // chunks per warp: 8 when there are enough chunks to give every SM `want` warps, fewer otherwise
-static int g_force_G = 0;   // tests: option "chunks_per_warp" pins G (small inputs otherwise always run with G = 1)
-void set_chunks_per_warp(int g) { g_force_G = (g == 1 || g == 2 || g == 4 || g == 8) ? g : 0; }
-static int chunks_per_warp(int n_chunks, int n_sm)
+// (RecOpts::force_G, option "chunks_per_warp", pins it: small inputs otherwise always run with G = 1)
+static int chunks_per_warp(int n_chunks, int n_sm, const RecOpts &o)
 {
-    if (g_force_G) return g_force_G;
+    if (o.force_G == 1 || o.force_G == 2 || o.force_G == 4 || o.force_G == 8) return o.force_G;
     const int want = n_sm * 2;
     int G = 8;
     while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
@@ -716,7 +765,7 @@ static int chunks_per_warp(int n_chunks, int n_sm)
 // The tensor-path forward kernel gives each chunk only 4 lanes for the float GEMV of the span-1 step; above 32 states
 // that only pays off when every warp has its full 8 chunks, otherwise the one-chunk-per-warp kernel is used
 // (the backward pass has no float step and always takes the tensor path).
-bool mma_forward_pays(int n_chunks, int n_sm, int Mp) { return Mp == 32 || chunks_per_warp(n_chunks, n_sm) == 8; }
+bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o) { return Mp == 32 || chunks_per_warp(n_chunks, n_sm, o) == 8; }
 
 // register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
 static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
@@ -738,32 +787,37 @@ static void configure_once()
     set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared, 4));
     set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));
     set_attrs(k_backward_mma<1, kFragShared>, bwd_smem(1, kFragShared));
-    set_attrs(k_forward_mma<2, kFragShared>, fwd_smem(2, kFragShared));
+    set_attrs(k_forward_mma<2, kFragShared>, fwd_smem(2, kFragShared, 0));
     set_attrs(k_backward_mma<2, kFragShared>, bwd_smem(2, kFragShared));
-    set_attrs(k_forward_mma<4, kFragGlobal>, fwd_smem(4, kFragGlobal));
+    set_attrs(k_forward_mma<4, kFragGlobal>, fwd_smem(4, kFragGlobal, 0));
     set_attrs(k_backward_mma<4, kFragGlobal>, bwd_smem(4, kFragGlobal));
+    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+    set_attrs(k_recursions_mma<1, kFragReg>, mx(fwd_smem(1, kFragReg, 4), bwd_smem(1, kFragReg)));
+    set_attrs(k_recursions_mma<1, kFragShared>, mx(fwd_smem(1, kFragShared, 4), bwd_smem(1, kFragShared)));
+    set_attrs(k_recursions_mma<2, kFragShared>, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)));
+    set_attrs(k_recursions_mma<4, kFragGlobal>, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)));
 }
 
-void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
     configure_once();
-    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
     if (m.Mp == 32) {
-        const int nkc = cached_keys(m);
+        const int nkc = cached_keys(m, o);
         if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, G, nkc);
         else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared, nkc), st>>>(m, p, w, G, nkc);
     } else if (m.Mp == 64) {
-        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared), st>>>(m, p, w, G, 0);
+        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared, 0), st>>>(m, p, w, G, 0);
     } else {
-        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal), st>>>(m, p, w, G, 0);
+        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal, 0), st>>>(m, p, w, G, 0);
     }
 }
 
-void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, cudaStream_t st)
+void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
     configure_once();
-    const int G = chunks_per_warp(p.n_chunks, n_sm);
+    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
     if (m.Mp == 32) {
         if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, G);
@@ -773,6 +827,30 @@ void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm,
     } else {
         k_backward_mma<4, kFragGlobal><<<blocks, kMW * 32, bwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
     }
+}
+
+// forward + backward in one launch (pass 0); returns false when this input takes separate kernels
+bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
+{
+    if (o.fused == 0 || !mma_forward_pays(p.n_chunks, n_sm, m.Mp, o)) return false;
+    configure_once();
+    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
+    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    const int layer = (n_sm % 2 == 0) ? n_sm : 0;
+    const int grid = layer ? ((2 * blocks + layer - 1) / layer) * layer : 2 * blocks;
+    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+    if (m.Mp == 32) {
+        const int nkc = cached_keys(m, o);
+        if (use_reg_frags(warps, n_sm))
+            k_recursions_mma<1, kFragReg><<<grid, kMW * 32, mx(fwd_smem(1, kFragReg, nkc), bwd_smem(1, kFragReg)), st>>>(m, p, w, G, nkc, blocks, layer);
+        else
+            k_recursions_mma<1, kFragShared><<<grid, kMW * 32, mx(fwd_smem(1, kFragShared, nkc), bwd_smem(1, kFragShared)), st>>>(m, p, w, G, nkc, blocks, layer);
+    } else if (m.Mp == 64) {
+        k_recursions_mma<2, kFragShared><<<grid, kMW * 32, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)), st>>>(m, p, w, G, 0, blocks, layer);
+    } else {
+        k_recursions_mma<4, kFragGlobal><<<grid, kMW * 32, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)), st>>>(m, p, w, G, 0, blocks, layer);
+    }
+    return true;
 }
 
 }  // namespace smcb

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
     const int K = m.K, NE = m.n_eig;
     const int slab = blockIdx.x;
     const int t = p.sl_contig[slab], s0 = p.sl_start[slab];
-    const uint32_t mask = p.sl_mask[slab];
+    const bool has_sites = mask_bit(p.sl_mask + (size_t)slab * p.mask_words, 0);
     const int64_t g0 = p.blk_off[t];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, 
     };
 
     // ================= span-1 blocks: X and the per-key gamma sums =================
-    if (mask & 1u) {
+    if (has_sites) {
         for (int x = tid; x < K * 32; x += kS32Warps * 32) gs[x] = 0.0;
         if (lane < 2) bkey[warp * 2 + lane] = -1;
         __syncthreads();
@@ -431,8 +431,7 @@ __global__ void __launch_bounds__(kSTWarps * 32, 2) k_statsT(Model m, Plan p, Wo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = m.K, NE = m.n_eig;
     const int slab = blockIdx.x;
-    const uint32_t mask = p.sl_mask[slab];
-    if (!(mask & 1u)) return;
+    if (!mask_bit(p.sl_mask + (size_t)slab * p.mask_words, 0)) return;
     const int t = p.sl_contig[slab], s0 = p.sl_start[slab];
     const int64_t g0 = p.blk_off[t];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -253,8 +253,124 @@ def test_many_keys_two_populations():
     assert abs(out["ll"][0] - o["ll"]) <= LL_RTOL * abs(o["ll"])
     for k in ("xisum", "gamma0", "gamma_sums"):
         assert relmax(out[k][0], o[k]) <= STAT_RTOL, k
-    assert np.array_equal(out["key_present"][0], (o["gamma_sums"] != 0).any(1) | out["key_present"][0].astype(bool))
+    # gamma_sums holds exactly the keys that occur in the contig (reference src/hmm.cpp:51-53, 69)
+    occurs = np.array([(obs[:, 1:] == keys[k]).all(1).any() for k in range(K)])
+    assert np.array_equal(out["key_present"][0].astype(bool), occurs)
+    assert np.array_equal((o["gamma_sums"] != 0).any(1), occurs)
     ctx.close()
+
+
+def random_model(rng, M, obs_list):
+    """A symmetric doubly stochastic chain (Sinkhorn) with the reference's uniform mixing (so that diag(e) T^T is similar
+    to a symmetric matrix and every eigensystem is real), emissions in (0, 1], eigensystems by the library's host routine."""
+    keys = np.unique(np.concatenate([c[:, 1:] for c in obs_list]), axis=0)
+    K = keys.shape[0]
+    base = rng.random((M, M)) ** 4 + np.eye(M) * 50
+    S = base + base.T
+    for _ in range(200):
+        d = S.sum(1)
+        S = S / np.sqrt(d[:, None] * d[None, :])
+    T = (1 - 1e-5) * S + 1e-5 / (M + 1)
+    pi = rng.random(M) + 0.1
+    pi /= pi.sum()
+    E = np.clip(rng.random((K, M)) * 0.9 + 0.05, 1e-3, 1.0)
+    lut = {tuple(int(v) for v in k): i for i, k in enumerate(keys)}
+    big = set()
+    for c in obs_list:
+        for row in np.unique(c[c[:, 0] > 1][:, 1:], axis=0):
+            big.add(lut[tuple(int(v) for v in row)])
+    eig_idx = np.array(sorted(big), np.int32)
+    eig = capi.host_eigensystems(T, E, eig_idx)
+    return {"pi": pi, "T": T, "E": E, "keys": keys, **eig}
+
+
+def check_against_port(out, obs_list, ref):
+    for c, obs in enumerate(obs_list):
+        o = port.hmm_estep(obs, ref)
+        assert abs(out["ll"][c] - o["ll"]) <= LL_RTOL * abs(o["ll"])
+        for k in ("xisum", "gamma0", "gamma_sums"):
+            assert relmax(out[k][c], o[k]) <= STAT_RTOL, k
+
+
+def test_more_than_30_keys_with_span_above_one():
+    """The reference builds one eigensystem per key that occurs with span > 1, without a cap (src/transition_bundle.cpp:14-25);
+    round 1 stopped at 30 (5 bits of the block code, 32-bit slab masks)."""
+    M, L = 16, 4000
+    rng = np.random.default_rng(31)
+    obs = np.zeros((L, 4), np.int32)
+    obs[:, 0] = 1
+    obs[0, 1] = -1
+    run = np.arange(1, L, 2)
+    obs[run, 0] = rng.integers(2, 40, size=run.size)
+    pick = rng.integers(0, 45, size=run.size)                   # 45 different keys carry spans > 1
+    obs[run, 1] = pick % 3
+    obs[run, 2] = 1 + pick // 3
+    obs[run, 3] = 20
+    site = np.arange(2, L, 2)
+    obs[site, 1] = rng.choice([1, 2, -1], size=site.size)
+    ref = random_model(rng, M, [obs])
+    assert len(ref["eig_key_idx"]) == 45 and not ref["eig_cplx"].any()
+    for opts in ({"chunk_blocks": 200, "burn_in_blocks": 512}, {"chunk_blocks": 128, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": 1},
+                 {"force_sequential": 1}):
+        ctx, out = run_ctx([obs], 1, ref, opts)
+        assert len(ctx.eig_keys) == 45
+        check_against_port(out, [obs], ref)
+        ctx.close()
+
+
+def test_more_than_2047_observation_keys():
+    """Round 1 packed the key id into 11 bits; two-population full-SFS data exceed that."""
+    M, L = 32, 9000
+    rng = np.random.default_rng(2048)
+    obs = np.zeros((L, 7), np.int32)
+    obs[:, 0] = 1
+    obs[0, 1] = -1
+    obs[0, 4] = -1
+    run = np.arange(1, L, 2)
+    obs[run, 0] = rng.integers(2, 300, size=run.size)
+    site = np.arange(2, L, 2)
+    combo = rng.permutation(61 * 61 - 2)[:site.size] + 1          # distinct (b1, b2) pairs, never (0, 0) or (60, 60)
+    obs[site, 1] = rng.integers(0, 3, size=site.size)
+    obs[site, 2] = combo // 61
+    obs[site, 3] = 60
+    obs[site, 5] = combo % 61
+    obs[site, 6] = 60
+    ref = random_model(rng, M, [obs])
+    assert ref["keys"].shape[0] > 2047
+    ctx, out = run_ctx([obs], 2, ref, {"chunk_blocks": 512, "burn_in_blocks": 512, "mma_min_chunks": 1})
+    assert ctx.K == ref["keys"].shape[0]
+    check_against_port(out, [obs], ref)
+    ctx.close()
+
+
+def test_exhausted_repair_sweeps_are_an_error():
+    """With boundaries still failing when max_sweeps is reached the results are wrong: estep() must say so (round 1 returned 0)."""
+    g = Golden("c2_1500")
+    ctx = capi.Context(0)
+    for k, v in {"chunk_blocks": 50, "burn_in_blocks": 0, "max_sweeps": 2}.items():
+        ctx.set_option(k, v)
+    ctx.set_contigs(g.contigs, g.npop)
+    with pytest.raises(RuntimeError, match="max_sweeps"):
+        ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    assert ctx.stats()["converged"] == 0
+    ctx.set_option("max_sweeps", 1 << 20)
+    out = ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    assert ctx.stats()["converged"] == 1
+    check_against(out, g.ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_fused_and_separate_recursion_launches_agree_bitwise(fused):
+    g = Golden("c4_twopop_1200")
+    opts = {"chunk_blocks": 100, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": 1, "chunks_per_warp": 8}
+    ctx, a = run_ctx(g.contigs, g.npop, g.ref, dict(opts, fused_recursions=fused))
+    ctx2, b = run_ctx(g.contigs, g.npop, g.ref, dict(opts, fused_recursions=1 - fused))
+    for k in ("ll", "xisum", "gamma0", "gamma_sums", "reduced"):
+        assert np.array_equal(a[k], b[k]), k
+    check_against(a, g.ref)
+    ctx.close()
+    ctx2.close()
 
 
 @pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_harness did not travel to this box")

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/smcpp_b200.h but not exported"
-    assert lib.smcpp_b200_abi_version() == 1
+    assert lib.smcpp_b200_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
