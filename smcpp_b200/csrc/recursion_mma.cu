@@ -686,27 +686,18 @@ __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work
 
 // Both recursions in ONE launch: the forward and the backward pass are independent (the statistics need both), and they
 // complement each other on an SM -- the forward pass spends half of its rounds on the FP32 pipe (float step), the backward
-// pass lives on the FP64 tensor pipe.  A CTA is either a forward or a backward CTA.  CTAs are handed to the SMs in
-// layers of n_sm consecutive block indices, so the role alternates with the block index AND flips from layer to layer:
-// every SM gets the same number of CTAs of each role (with `role = bid & 1` an even SM count would give half of the
-// SMs forward CTAs only).  This replaces two streams + an event + a host synchronisation between setup and recursions
-// (two kernels enqueued behind running setup kernels started one after the other instead of side by side).
+// pass lives on the FP64 tensor pipe.  A CTA is either a forward or a backward CTA: the first `blocks` CTAs are the
+// backward pass, the rest the forward pass.  The hardware hands CTAs to the SMs in block-index order, so every SM gets
+// its share of both, and the forward warps -- the longer pass -- land in the higher warp slots, which the issue
+// arbiter favours (interleaving the roles by block index gave the backward pass the priority: 8.2 ms instead of 7.65 ms
+// for the recursion phase of the benchmark).  This replaces two streams + an event + a host synchronisation between setup
+// and recursions (two kernels enqueued behind running setup kernels started one after the other instead of side by side).
 template <int NS, int FRAG>
-__global__ void __launch_bounds__(kMW * 32) k_recursions_mma(Model m, Plan p, Work w, int G, int nkc, int blocks, int layer)
+__global__ void __launch_bounds__(kMW * 32) k_recursions_mma(Model m, Plan p, Work w, int G, int nkc, int blocks)
 {
     const int bid = blockIdx.x;
-    int role, idx;
-    if (layer > 0) {
-        const int L = bid / layer, pos = bid - L * layer;
-        role = (pos + L) & 1;
-        idx = L * (layer >> 1) + (pos >> 1);
-    } else {
-        role = bid & 1;
-        idx = bid >> 1;
-    }
-    if (idx >= blocks) return;
-    if (role == 0) forward_mma_body<NS, FRAG>(m, p, w, G, nkc, idx);
-    else backward_mma_body<NS, FRAG>(m, p, w, G, idx);
+    if (bid < blocks) backward_mma_body<NS, FRAG>(m, p, w, G, bid);
+    else forward_mma_body<NS, FRAG>(m, p, w, G, nkc, bid - blocks);
 }
 
 // ---- launch -------------------------------------------------------------------------------------------------
@@ -836,19 +827,18 @@ bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_s
     configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
-    const int layer = (n_sm % 2 == 0) ? n_sm : 0;
-    const int grid = layer ? ((2 * blocks + layer - 1) / layer) * layer : 2 * blocks;
+    const int grid = 2 * blocks;
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
     if (m.Mp == 32) {
         const int nkc = cached_keys(m, o);
         if (use_reg_frags(warps, n_sm))
-            k_recursions_mma<1, kFragReg><<<grid, kMW * 32, mx(fwd_smem(1, kFragReg, nkc), bwd_smem(1, kFragReg)), st>>>(m, p, w, G, nkc, blocks, layer);
+            k_recursions_mma<1, kFragReg><<<grid, kMW * 32, mx(fwd_smem(1, kFragReg, nkc), bwd_smem(1, kFragReg)), st>>>(m, p, w, G, nkc, blocks);
         else
-            k_recursions_mma<1, kFragShared><<<grid, kMW * 32, mx(fwd_smem(1, kFragShared, nkc), bwd_smem(1, kFragShared)), st>>>(m, p, w, G, nkc, blocks, layer);
+            k_recursions_mma<1, kFragShared><<<grid, kMW * 32, mx(fwd_smem(1, kFragShared, nkc), bwd_smem(1, kFragShared)), st>>>(m, p, w, G, nkc, blocks);
     } else if (m.Mp == 64) {
-        k_recursions_mma<2, kFragShared><<<grid, kMW * 32, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)), st>>>(m, p, w, G, 0, blocks, layer);
+        k_recursions_mma<2, kFragShared><<<grid, kMW * 32, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)), st>>>(m, p, w, G, 0, blocks);
     } else {
-        k_recursions_mma<4, kFragGlobal><<<grid, kMW * 32, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)), st>>>(m, p, w, G, 0, blocks, layer);
+        k_recursions_mma<4, kFragGlobal><<<grid, kMW * 32, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)), st>>>(m, p, w, G, 0, blocks);
     }
     return true;
 }

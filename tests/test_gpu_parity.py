@@ -320,7 +320,7 @@ def test_more_than_30_keys_with_span_above_one():
 
 def test_more_than_2047_observation_keys():
     """Round 1 packed the key id into 11 bits; two-population full-SFS data exceed that."""
-    M, L = 32, 9000
+    M, L = 32, 7000
     rng = np.random.default_rng(2048)
     obs = np.zeros((L, 7), np.int32)
     obs[:, 0] = 1
