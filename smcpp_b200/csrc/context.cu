@@ -73,9 +73,9 @@ template <typename T> struct PinBuf {
 
 struct smcpp_b200_ctx {
     int device = 0;
-    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_setup_done = nullptr, ev_bwd_done = nullptr;
+    cudaEvent_t ev_setup_done = nullptr, ev_bwd_done = nullptr, ev_fwd_done = nullptr;
     std::string err;
 
     // ---- dataset (set_contigs)
@@ -259,7 +259,8 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device)
     ctx->device = device;
     DeviceGuard guard(device);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->st3, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
         delete ctx;
         return 1;
@@ -271,6 +272,7 @@ int smcpp_b200_create(smcpp_b200_ctx **out, int device)
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&ctx->ev_setup_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_bwd_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fwd_done, cudaEventDisableTiming);
     *out = ctx;
     return 0;
 }
@@ -303,8 +305,10 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_setup_done) cudaEventDestroy(ctx->ev_setup_done);
     if (ctx->ev_bwd_done) cudaEventDestroy(ctx->ev_bwd_done);
+    if (ctx->ev_fwd_done) cudaEventDestroy(ctx->ev_fwd_done);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->st2) cudaStreamDestroy(ctx->st2);
+    if (ctx->st3) cudaStreamDestroy(ctx->st3);
     delete ctx;
 }
 
@@ -329,6 +333,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "chunks_per_warp") ctx->rec.force_G = (int)value;           // 0 = automatic
     else if (n == "fwd_cached_keys") ctx->rec.cached_keys = std::max(0, std::min(4, (int)value));
     else if (n == "fused_recursions") ctx->rec.fused = value != 0;
+    else if (n == "tiles") ctx->rec.tiles = value >= 2 ? 2 : 1;
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;
@@ -550,10 +555,12 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             // full ones set the pace (3 contigs x 10^6 blocks: 5 862 chunks 3.14 ms, 4 734 chunks 2.18 ms).  One or two
             // CTAs per SM and kernel: measured cost of one chunk step at M = 32 is ~3 750 cycles with one CTA of each
             // kernel on an SM and ~5 460 with two (profiles/r1h), so the shorter schedule wins below ~4 x 10^6 blocks.
-            const int per_layer = ctx->n_sm * 32;
+            const bool two_tiles = Mp == 32 && ctx->rec.tiles == 2;          // recursion_mma2.cu: 16 chunks per warp
+            const int per_layer = ctx->n_sm * (two_tiles ? tiles_chunks_per_cta(2) : 32);
             // inputs too small to fill the warps with 8 chunks each keep the burn-in as the lower bound
             if (chunks_for(min_lc_for(per_layer)) < ctx->n_sm * 8) relaxed = false;
-            const int layers = std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp, ctx->rec), ctx->n_sm * 8) / (ctx->n_sm * 4)));
+            // (the two-tile kernels need most of the register file: one CTA of each pass per SM)
+            const int layers = two_tiles ? 1 : std::max(1, std::min(2, std::min(resident_warps_mma(ctx->n_sm, Mp, ctx->rec), ctx->n_sm * 8) / (ctx->n_sm * 4)));
             const double step_cost[3] = {0.0, 3750.0, 5460.0};
             double best = 0.0;
             Lc = 0;
@@ -873,23 +880,38 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     const bool mma = (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
     ctx->use_mma = mma;
     const bool fwd_mma = mma && (ctx->opt_force_mma_forward || mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp, ctx->rec));
+    const bool tiles = fwd_mma && m.Mp == 32 && ctx->rec.tiles == 2;
     cudaEventRecord(ctx->ev[5], ctx->st);
-    if (fwd_mma && launch_recursions_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st)) {
+    if (ctx->rec.fused && tiles && launch_recursions_tiles(m, p, w, ctx->n_sm, ctx->rec, ctx->st, ctx->st)) {
+        ctx->stats.kernel_launches += 1;
+        cudaEventRecord(ctx->ev[6], ctx->st);
+        cudaEventRecord(ctx->ev[7], ctx->st);
+    } else if (ctx->rec.fused && fwd_mma && !tiles && launch_recursions_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st)) {
         // forward and backward recursion in one launch
         ctx->stats.kernel_launches += 1;
         cudaEventRecord(ctx->ev[6], ctx->st);
         cudaEventRecord(ctx->ev[7], ctx->st);
     } else {
-        // two launches on two streams: the backward recursion does not depend on alpha
+        // Two launches on two side streams that BOTH wait for the setup work of the main stream: the recursions are
+        // independent (the backward pass does not read alpha), and they must start together -- a kernel enqueued in
+        // order behind the setup kernels starts first and takes the SMs for itself, the other one then runs behind it
+        // instead of beside it (round 1 drained the setup work with a host synchronisation instead).
         cudaEventRecord(ctx->ev_setup_done, ctx->st);
         CU(cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0));
+        CU(cudaStreamWaitEvent(ctx->st3, ctx->ev_setup_done, 0));
         cudaEventRecord(ctx->ev[5], ctx->st2);
-        if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
+        if (tiles && launch_recursions_tiles(m, p, w, ctx->n_sm, ctx->rec, ctx->st3, ctx->st2)) {
+            // both kernels are enqueued (backward first)
+        } else {
+            if (mma) launch_backward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st2); else launch_backward(m, p, w, 0, ctx->st2);
+            if (fwd_mma) launch_forward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st3); else launch_forward(m, p, w, 0, ctx->st3);
+        }
         cudaEventRecord(ctx->ev[6], ctx->st2);
-        if (fwd_mma) launch_forward_mma(m, p, w, ctx->n_sm, ctx->rec, ctx->st); else launch_forward(m, p, w, 0, ctx->st);
-        cudaEventRecord(ctx->ev[7], ctx->st);
         cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
+        cudaEventRecord(ctx->ev_fwd_done, ctx->st3);
         CU(cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0));
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_fwd_done, 0));
+        cudaEventRecord(ctx->ev[7], ctx->st);
         ctx->stats.kernel_launches += 2;
     }
     launch_check_backward(m, p, w, ctx->opt_bwd_tol, ctx->st);

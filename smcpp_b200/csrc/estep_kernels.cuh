@@ -155,8 +155,12 @@ struct RecOpts {             // per-context tuning of the tensor-path recursions
     int cached_keys = 0;     // span-1 keys whose float step matrix is resident in shared memory (M <= 32), 0..4 (measured: no gain, the
                              // LSU data pipe carries the same bytes into the registers either way)
     int force_G = 0;         // chunks per warp pinned to 1 / 2 / 4 / 8 (0 = automatic)
-    int fused = 1;           // forward and backward recursion in one launch (k_recursions_mma)
+    int fused = 0;           // forward and backward recursion in one launch (measured slower than two streams: 8.2 vs 7.65 ms on C3)
+    int tiles = 2;           // MMA row tiles per warp at M <= 32 (recursion_mma2.cu): 2 = 16 chunks per warp, 1 = recursion_mma.cu
 };
+// M <= 32, several row tiles per warp (recursion_mma2.cu); st_fwd == st_bwd selects the one-launch form
+bool launch_recursions_tiles(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st_fwd, cudaStream_t st_bwd);
+int tiles_chunks_per_cta(int NM);
 bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);
 void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);   // Mp in {32, 64, 128}, pass 0, <= 8 chunks / warp
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);

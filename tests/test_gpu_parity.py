@@ -62,13 +62,33 @@ def test_golden_chunked(name, chunk, burn):
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)     # M = 16, 17, 32 (one 32-state tile), 51, 64 (two tiles)
 @pytest.mark.parametrize("chunk,burn", [(64, 64), (100, 512), (37, 300), (16, 0)])
-def test_golden_chunked_tensor_path(name, chunk, burn):
-    """The 8-chunks-per-warp DMMA recursions (recursion32_mma.cu), forced on for small inputs."""
+@pytest.mark.parametrize("tiles", [1, 2])
+def test_golden_chunked_tensor_path(name, chunk, burn, tiles):
+    """The DMMA recursions, forced on for small inputs: 8 chunks per warp (recursion_mma.cu, tiles = 1) and, for M <= 32,
+    16 chunks per warp (recursion_mma2.cu, tiles = 2)."""
     g = Golden(name)
     ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": chunk, "burn_in_blocks": burn, "mma_min_chunks": 1,
-                                                   "force_mma_forward": 1})
+                                                   "force_mma_forward": 1, "tiles": tiles})
     check_against(out, g.ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1_2k", "c2_1500", "m17_800", "c4_twopop_1200", "ragged"])
+@pytest.mark.parametrize("G,fused", [(8, 0), (8, 1), (2, 0), (1, 1)])
+def test_two_tile_recursions_are_bitwise_the_one_tile_recursions(name, G, fused):
+    """Per chunk the two-tile kernels execute the one-tile kernels' arithmetic (same fragments, same order): identical
+    results for identical chunking, whatever the chunks-per-tile count and the launch form."""
+    g = Golden(name)
+    opts = {"chunk_blocks": 48, "burn_in_blocks": 512, "mma_min_chunks": 1, "force_mma_forward": 1, "chunks_per_warp": G}
+    ctx1, a = run_ctx(g.contigs, g.npop, g.ref, dict(opts, tiles=1))
+    ctx2, b = run_ctx(g.contigs, g.npop, g.ref, dict(opts, tiles=2, fused_recursions=fused))
+    for k in ("ll", "xisum", "gamma0", "gamma_sums", "reduced"):
+        assert np.array_equal(a[k], b[k]), k
+    for c in range(len(g.contigs)):
+        assert np.array_equal(ctx1.debug_alpha_hat(c), ctx2.debug_alpha_hat(c))
+    check_against(b, g.ref)
+    ctx1.close()
+    ctx2.close()
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)

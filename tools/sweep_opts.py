@@ -24,6 +24,7 @@ def main():
     w = synth.config(cfg)
     contigs = w.contigs[:int(ncont)] if ncont else w.contigs
     steps = int(os.environ.get("SWEEP_STEPS", "5"))
+    upload = os.environ.get("SWEEP_UPLOAD", "0") == "1"      # 1: every step uploads the inputs and lets the library compute the eigensystems
     ll0 = None
     for s in sets:
         ctx = capi.Context(0)
@@ -37,7 +38,7 @@ def main():
             ctx.estep_device(model["pi"], model["T"], model["E"], model, upload=False)
         acc = {}
         for _ in range(steps):
-            ctx.estep_device(model["pi"], model["T"], model["E"], model, upload=False)
+            ctx.estep_device(model["pi"], model["T"], model["E"], None if upload else model, upload=upload)
             st = ctx.stats()
             for k in ("ms_total", "ms_forward", "ms_forward_only", "ms_backward", "ms_stats", "ms_finalize"):
                 acc.setdefault(k, []).append(st[k])
