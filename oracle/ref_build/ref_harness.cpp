@@ -124,6 +124,27 @@ static int run(const smcb::Bundle &in, smcb::Bundle &out, int threads, int repea
     im->saveGamma = save_gamma != 0;
     // rebuilds of pi / emission table / T are not part of the timed E-step window
     im->do_dirty_work();
+    // Optional overrides of what do_dirty_work() left behind (tests of irregular spectra: the reference's own model never
+    // produces a transition matrix whose diag(e) Td^T has complex or negative eigenvalues, HMM::Estep handles any input):
+    //   override_T [M][M] row-major, override_E [K][M] in the std::map order of emission_probs, override_pi [M]
+    if (in.has("override_T")) {
+        const double *t = in.get("override_T").as<double>();
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) im->transition(i, j) = adouble(t[(size_t)i * M + j]);
+        im->tb.update(im->transition, false);
+    }
+    if (in.has("override_E")) {
+        const double *e = in.get("override_E").as<double>();
+        size_t k = 0;
+        for (auto &pr : im->emission_probs) {
+            for (int mm = 0; mm < M; ++mm) pr.second(mm) = adouble(e[k * M + mm]);
+            ++k;
+        }
+    }
+    if (in.has("override_pi")) {
+        const double *v = in.get("override_pi").as<double>();
+        for (int mm = 0; mm < M; ++mm) im->pi(mm) = adouble(v[mm]);
+    }
 
     std::vector<double> secs;
     for (int r = 0; r < repeat; ++r) {

@@ -127,6 +127,7 @@ struct smcpp_b200_ctx {
     int opt_max_sweeps = 1 << 30;
     int opt_force_sequential = 0;
     int opt_force_mma_forward = 0;  // tests: take the tensor-path forward kernel even where mma_forward_pays() says no
+    int opt_stats_streams = 2;      // 2: span-1 and span>1 statistics kernels on two streams
     int opt_mma_min_chunks = 64;    // use the 8-chunks-per-warp tensor-path recursions from this many chunks on
     int burn_in_adapt = 0;          // grows when boundary checks fail (sticky between E-steps)
     RecOpts rec;                    // tensor-path recursion tuning (chunks per warp, resident step matrices)
@@ -334,6 +335,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "fwd_cached_keys") ctx->rec.cached_keys = std::max(0, std::min(4, (int)value));
     else if (n == "fused_recursions") ctx->rec.fused = value != 0;
     else if (n == "tiles") ctx->rec.tiles = value >= 2 ? 2 : 1;
+    else if (n == "stats_streams") ctx->opt_stats_streams = value >= 2 ? 2 : 1;
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;
@@ -799,7 +801,17 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
 static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, const Plan &p, const Work &w)
 {
     cudaEventRecord(ctx->ev[2], ctx->st);
-    launch_stats(m, p, w, ctx->st);
+    const bool split = ctx->opt_stats_streams == 2 && (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0;
+    if (split) {
+        // the span-1 and the span>1 statistics kernels are independent: side by side on two streams
+        cudaEventRecord(ctx->ev_setup_done, ctx->st);
+        cudaStreamWaitEvent(ctx->st2, ctx->ev_setup_done, 0);
+        launch_stats(m, p, w, ctx->st, ctx->st2);
+        cudaEventRecord(ctx->ev_bwd_done, ctx->st2);
+        cudaStreamWaitEvent(ctx->st, ctx->ev_bwd_done, 0);
+    } else {
+        launch_stats(m, p, w, ctx->st, ctx->st);
+    }
     cudaEventRecord(ctx->ev[3], ctx->st);
     ctx->stats.kernel_launches += ((m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0) ? 2 : 1;
     ctx->gamma_valid = false;

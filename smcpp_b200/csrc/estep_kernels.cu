@@ -609,10 +609,10 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
     }
 }
 
-void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs)
 {
-    if (m.Mp == 32) { launch_stats32(m, p, w, st); return; }
-    if (m.Mp == 64 || m.Mp == 128) { launch_stats64(m, p, w, st); return; }
+    if (m.Mp == 32) { launch_stats32(m, p, w, st, st_runs); return; }
+    if (m.Mp == 64 || m.Mp == 128) { launch_stats64(m, p, w, st, st_runs); return; }
     const int smem = stats_smem_bytes(m);
     // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
     static std::atomic<size_t> configured[5][kMaxDevices];

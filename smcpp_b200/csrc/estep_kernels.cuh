@@ -146,8 +146,8 @@ void launch_forward32(const Model &m, const Plan &p, const Work &w, int pass, cu
 void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);  // Mp == 32
 size_t sums_stride(const Model &m);
 int resident_warps32(int n_sm);
-void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 32
-void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st);          // Mp == 64
+void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);          // Mp == 32
+void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);          // Mp == 64
 constexpr int kItemBlocks = 4096;   // span>1 blocks per work item of k_stats32e
 void launch_setup_pwtab(const Model &m, int n_sm, cudaStream_t st);
 void launch_setup_frags(const Model &m, cudaStream_t st);                                      // Mp == 32
@@ -156,7 +156,8 @@ struct RecOpts {             // per-context tuning of the tensor-path recursions
                              // LSU data pipe carries the same bytes into the registers either way)
     int force_G = 0;         // chunks per warp pinned to 1 / 2 / 4 / 8 (0 = automatic)
     int fused = 0;           // forward and backward recursion in one launch (measured slower than two streams: 8.2 vs 7.65 ms on C3)
-    int tiles = 2;           // MMA row tiles per warp at M <= 32 (recursion_mma2.cu): 2 = 16 chunks per warp, 1 = recursion_mma.cu
+    int tiles = 1;           // MMA row tiles per warp at M <= 32: 1 = recursion_mma.cu (8 chunks per warp); 2 = recursion_mma2.cu (16 chunks per
+                             // warp: half the LSU traffic per chunk step, but 255 registers leave one warp per scheduler -- measured slower, 9.9 vs 7.6 ms)
 };
 // M <= 32, several row tiles per warp (recursion_mma2.cu); st_fwd == st_bwd selects the one-launch form
 bool launch_recursions_tiles(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st_fwd, cudaStream_t st_bwd);
@@ -169,7 +170,8 @@ bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);
-void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
+// st_runs: stream of the span>1 statistics kernel (independent of the span-1 kernel; == st runs them back to back)
+void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st);

@@ -30,6 +30,10 @@ namespace smcb {
 
 constexpr int kMW = 4;             // warps per CTA
 constexpr unsigned kAll = 0xffffffffu;
+#ifndef SMCB_STREAM_PW
+#define SMCB_STREAM_PW 1
+#endif
+constexpr bool kStreamPw = SMCB_STREAM_PW != 0;   // d~^span rows: ld.global.nc.L1::no_allocate
 
 __device__ __forceinline__ int st_of(int q, int idx) { return 8 * (idx >> 1) + 2 * q + (idx & 1); }
 
@@ -134,13 +138,22 @@ __device__ __forceinline__ void lds2p(const float *p, f32x2 &a, f32x2 &b)   // 1
 //   kAGeneric  per lane either of the two (generic 128-bit loads): the frequent keys' matrices are resident in shared
 //              memory, the rare ones (60+ full-SFS keys, 4 KB each) come through L1 / L2
 // ncu r2a: with all matrices in global memory the L1 hit rate is 54 % and 30 % of the kernel's samples wait on these loads.
-constexpr int kAGlobal = 0, kAShared = 1, kAGeneric = 2;
-__device__ __forceinline__ void ldgen2p(const float *p, f32x2 &a, f32x2 &b)   // 128-bit generic load of 4 floats as 2 packed pairs
+constexpr int kAGlobal = 0, kAShared = 1, kAMixed = 2;
+// One row part (8 floats) for a warp whose lanes are split between resident and non-resident keys: two PREDICATED loads
+// into the same registers -- lanes with a resident key read shared memory (4 distinct 16-byte pieces per warp instruction:
+// one LSU wavefront), the others the read-only path (their quads only) -- instead of one generic load whose slowest lane
+// and widest form set the cost for everybody.
+__device__ __forceinline__ void ld_row_mixed(f32x2x4 &r, const float *ps, const float *pg, bool in_smem)
 {
-    asm("ld.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %6, 0;\n"
+                 " @p ld.shared.v2.b64 {%0,%1}, [%4];\n @p ld.shared.v2.b64 {%2,%3}, [%4+16];\n"
+                 " @!p ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%5];\n}"
+                 : "+l"(r.v[0]), "+l"(r.v[1]), "+l"(r.v[2]), "+l"(r.v[3])
+                 : "r"((unsigned)__cvta_generic_to_shared(ps)), "l"(pg), "r"((int)in_smem));
 }
 template <int NS, int MODE>
-__device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32x2 (&y2)[4 * NS], f32x2 kNegZero2, f32x2 kOne2)
+__device__ __forceinline__ void float_gemv(const float *A, const float *Ag, bool in_smem, const float4 *xr, f32x2 (&y2)[4 * NS],
+                                           f32x2 kNegZero2, f32x2 kOne2)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS;
 #pragma unroll(NS == 1 ? 8 : 2)
@@ -150,13 +163,13 @@ __device__ __forceinline__ void float_gemv(const float *A, const float4 *xr, f32
         for (int cidx = 0; cidx < 4; ++cidx) {
             const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
             const f32x2 xx = pack2(xi, xi);
-            const float *Ai = A + (size_t)(4 * i4 + cidx) * 4 * NI;
+            const size_t row = (size_t)(4 * i4 + cidx) * 4 * NI;
 #pragma unroll
             for (int h = 0; h < NS; ++h) {
                 f32x2x4 av;
-                if (MODE == kAShared) { lds2p(Ai + 8 * h, av.v[0], av.v[1]); lds2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
-                else if (MODE == kAGeneric) { ldgen2p(Ai + 8 * h, av.v[0], av.v[1]); ldgen2p(Ai + 8 * h + 4, av.v[2], av.v[3]); }
-                else av = ldg256p(Ai + 8 * h);
+                if (MODE == kAShared) { lds2p(A + row + 8 * h, av.v[0], av.v[1]); lds2p(A + row + 8 * h + 4, av.v[2], av.v[3]); }
+                else if (MODE == kAMixed) { av.v[0] = av.v[1] = av.v[2] = av.v[3] = 0ull; ld_row_mixed(av, A + row + 8 * h, Ag + row + 8 * h, in_smem); }
+                else av = ldg256p(Ag + row + 8 * h);
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2)   // two columns per instruction
                     y2[4 * h + j2] = fma2(fma2(xx, av.v[j2], kNegZero2), kOne2, y2[4 * h + j2]);
@@ -231,6 +244,12 @@ __device__ __forceinline__ void ldg_if(int &dst, const int32_t *ptr, bool pred)
 __device__ __forceinline__ void ldg_if(int &dst, const kcode_t *ptr, bool pred)
 {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p ld.global.nc.b32 %0, [%1];\n}" : "+r"(dst) : "l"(ptr), "r"((int)pred));
+}
+__device__ __forceinline__ double2 ldg_stream2(const double2 *p)   // read-only, no L1 allocation (single-use table rows)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
 }
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
@@ -338,7 +357,7 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
     auto load_pw = [&]() {   // states st(q, 2nt), st(q, 2nt + 1) of the q-major table
         const double2 *pw = reinterpret_cast<const double2 *>(m.pwq + ((size_t)((kc >> kKeyBits) - 1) * m.n_span + sid) * MP + q * NI);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) pwv[nt] = __ldg(pw + nt);
+        for (int nt = 0; nt < NT; ++nt) pwv[nt] = kStreamPw ? ldg_stream2(pw + nt) : __ldg(pw + nt);
     };
     fetch_cur();
     if (active && (kc >> kKeyBits) > 0) load_pw();
@@ -401,12 +420,13 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
                 if (k == m.hot_keys[sl]) slot = sl;
             // row i: + i * 4 * NI floats; this lane's NI columns are contiguous
             const float *Ag = m.A32q + ((size_t)k * MP * 4 + q) * NI;
+            const float *As = s_A + (size_t)(slot >= 0 ? slot : 0) * MM + q * NI;
             if (nkc == 0) {
-                float_gemv<NS, kAGlobal>(Ag, xr, y2, m.c_negzero2, m.c_one2);
+                float_gemv<NS, kAGlobal>(As, Ag, false, xr, y2, m.c_negzero2, m.c_one2);
             } else if (__all_sync(kAll, slot >= 0)) {
-                float_gemv<NS, kAShared>(s_A + (size_t)slot * MM + q * NI, xr, y2, m.c_negzero2, m.c_one2);
+                float_gemv<NS, kAShared>(As, Ag, true, xr, y2, m.c_negzero2, m.c_one2);
             } else {
-                float_gemv<NS, kAGeneric>(slot >= 0 ? s_A + (size_t)slot * MM + q * NI : Ag, xr, y2, m.c_negzero2, m.c_one2);
+                float_gemv<NS, kAMixed>(As, Ag, slot >= 0, xr, y2, m.c_negzero2, m.c_one2);
             }
             float y[NI];
 #pragma unroll
@@ -572,7 +592,7 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
         const double *row = ty > 0 ? m.pwq + ((size_t)(ty - 1) * m.n_span + sid) * MP : m.Eq + (size_t)(kc & kKeyMask) * MP;
         const double2 *src = reinterpret_cast<const double2 *>(row + q * NI);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) opv[nt] = __ldg(src + nt);
+        for (int nt = 0; nt < NT; ++nt) opv[nt] = (kStreamPw && ty > 0) ? ldg_stream2(src + nt) : __ldg(src + nt);
     };
     fetch_cur();
     if (active) load_op();
@@ -626,11 +646,14 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
         }
         // loose normalisation by an exact power of two (every statistic is invariant to beta's scale)
         ++since;
-        bool tiny = true;
+        // "the vector has become tiny": exponent of its largest entry, integer compares on the high words (eight DSETP per
+        // step on the FP64 pipe were 8 % of this kernel's samples, ncu r2a)
+        int hi = 0;
 #pragma unroll
-        for (int idx = 0; idx < NI; ++idx) tiny = tiny && !(fabs(nb[idx]) > 1e-100);
-        const int t1 = __shfl_xor_sync(kAll, (int)tiny, 1), t2 = __shfl_xor_sync(kAll, (int)tiny, 2), t3 = __shfl_xor_sync(kAll, (int)tiny, 3);
-        const bool need = adv && (since >= 4 || (t1 & t2 & t3 & (int)tiny));
+        for (int idx = 0; idx < NI; ++idx) hi = max(hi, __double2hiint(nb[idx]) & 0x7fffffff);
+        hi = max(hi, __shfl_xor_sync(kAll, hi, 1));
+        hi = max(hi, __shfl_xor_sync(kAll, hi, 2));
+        const bool need = adv && (since >= 4 || hi < 0x2b200000);      // largest |entry| < 2^-333 ~ 1e-100
         if (__any_sync(kAll, need)) {
             double part = 0.0;
 #pragma unroll

@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(kSTWarps * 32, 2) k_statsTe(Model m, Plan p, W
 }
 
 template <int NS>
-static void launch_statsT_impl(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+static void launch_statsT_impl(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs)
 {
     constexpr int MP = 32 * NS;
     const int in_smem = (size_t)m.K * MP * sizeof(double) <= (size_t)kSTMaxGsBytes ? 1 : 0;
@@ -724,13 +724,13 @@ static void launch_statsT_impl(const Model &m, const Plan &p, const Work &w, cud
     static std::atomic<size_t> configured[kMaxDevices];
     if (needs_smem_config(configured, smem)) cudaFuncSetAttribute(k_statsT<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_statsT<NS><<<p.n_slabs, kSTWarps * 32, smem, st>>>(m, p, w, in_smem);
-    if (p.n_items > 0) k_statsTe<NS><<<p.n_items, kSTWarps * 32, (size_t)kSTWarps * 32 * 33 * sizeof(double), st>>>(m, p, w);
+    if (p.n_items > 0) k_statsTe<NS><<<p.n_items, kSTWarps * 32, (size_t)kSTWarps * 32 * 33 * sizeof(double), st_runs>>>(m, p, w);
 }
 
-void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st)   // Mp in {64, 128}
+void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs)   // Mp in {64, 128}
 {
-    if (m.Mp == 64) launch_statsT_impl<2>(m, p, w, st);
-    else launch_statsT_impl<4>(m, p, w, st);
+    if (m.Mp == 64) launch_statsT_impl<2>(m, p, w, st, st_runs);
+    else launch_statsT_impl<4>(m, p, w, st, st_runs);
 }
 
 size_t stats32_smem_bytes(const Model &m)
@@ -740,7 +740,7 @@ size_t stats32_smem_bytes(const Model &m)
            (size_t)kS32Warps * 2 * sizeof(int);
 }
 
-void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs)
 {
     const size_t smem = stats32_smem_bytes(m);
     static std::atomic<size_t> configured[kMaxDevices];
@@ -750,7 +750,7 @@ void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t s
         const size_t smem_e = ((size_t)kSEWarps * 32 * 33 + (size_t)kSEWarps * 32) * sizeof(double);
         static std::atomic<size_t> configured_e[kMaxDevices];
         if (needs_smem_config(configured_e, smem_e)) cudaFuncSetAttribute(k_stats32e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
-        k_stats32e<<<p.n_items, kSEWarps * 32, smem_e, st>>>(m, p, w);
+        k_stats32e<<<p.n_items, kSEWarps * 32, smem_e, st_runs>>>(m, p, w);
     }
 }
 

@@ -28,6 +28,7 @@ class Workload:
     alpha: float = 1.0
     pol_err: float = 0.0
     sfs: np.ndarray = field(default=None)   # [M, 3, dim]
+    overrides: dict = field(default_factory=dict)   # test harness only: override_T / override_E / override_pi
 
     @property
     def total_blocks(self) -> int:
@@ -46,6 +47,7 @@ class Workload:
             "alpha": np.float64(self.alpha), "pol_err": np.float64(self.pol_err),
             "sfs": self.sfs,
             "save_gamma": np.int32(bool(save_gamma)), "dump_alpha": np.int32(bool(dump_alpha)),
+            **{k: np.asarray(v, np.float64) for k, v in self.overrides.items()},
         }
 
 
