@@ -150,6 +150,25 @@ int smcpp_b200_fetch(smcpp_b200_ctx *ctx, double *ll, double *xisum, double *gam
                      double *reduced);
 
 /*
+ * The M-step objective from the statistics that are resident on the device.
+ * Replaces: HMM::Q (reference src/hmm.cpp:155-193) summed over contigs by InferenceManager::Q
+ *           (src/inference_manager.cpp:116-126): per contig each term is accumulated in the reference's element order with
+ *           its doubly compensated summation (include/common.h:27-46), then the contigs are added in order.
+ *   q[4]  = { sum log(pi) gamma0,  sum_{keys with nb == 0} log(e_key) gamma_sums_key,  the same for nb > 0,  sum log(T) xisum },
+ *           keys present in the contig only (src/hmm.cpp:166-172); a present key with a non-positive emission entry makes
+ *           its class -infinity and ends the key loop (the reference warns there, :172-178).
+ *   n_deriv > 0: the reference evaluates Q on autodiff scalars; hand in the derivative arrays of the inputs,
+ *           dpi[n_deriv][M], dT[n_deriv][M][M], dE[n_deriv][K][M], and get dq[4][n_deriv] (d log x = dx / x contracted with the
+ *           same statistics in the same order).  pi, T, E are the CURRENT model's (the M-step evaluates Q many times per E-step).
+ * set_statistics loads per-contig statistics instead of computing them -- the reference's HMM constructor pre-fill
+ * (gamma_sums = span * pi per key, xisum = gamma0 = 0: src/hmm.cpp:16-27, Q() before the first E-step) or a checkpoint.
+ */
+int smcpp_b200_q(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_deriv, const double *dpi,
+                 const double *dT, const double *dE, double *q /* 4 */, double *dq /* 4 * n_deriv, or NULL */);
+int smcpp_b200_set_statistics(smcpp_b200_ctx *ctx, int M, const double *xisum /* C*M*M */, const double *gamma0 /* C*M */,
+                              const double *gamma_sums /* C*K*M */);
+
+/*
  * Full posterior decoding, the `smc++ posterior` variant of the E-step.
  * Replaces: InferenceManager::saveGamma + the per-block gamma columns of HMM::Estep (reference
  *           include/inference_manager.h:40, src/hmm.cpp:48-49, 116-121, 134-136, 147-150) and getGammas()

@@ -45,7 +45,7 @@ SYMBOLS = [
     "smcpp_b200_host_emission",
     "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
     "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat", "smcpp_b200_set_save_gamma",
-    "smcpp_b200_fetch_gamma",
+    "smcpp_b200_fetch_gamma", "smcpp_b200_q", "smcpp_b200_set_statistics",
     "smcpp_b200_obs_create", "smcpp_b200_obs_destroy", "smcpp_b200_obs_last_error", "smcpp_b200_obs_upload", "smcpp_b200_obs_thin",
     "smcpp_b200_obs_bin", "smcpp_b200_obs_recode_monomorphic", "smcpp_b200_obs_compress", "smcpp_b200_obs_rows", "smcpp_b200_obs_last_ms",
     "smcpp_b200_obs_download", "smcpp_b200_obs_recode_nonseg", "smcpp_b200_obs_break_long_spans", "smcpp_b200_obs_piece_offsets",
@@ -280,6 +280,37 @@ class Context:
                                            ptr(out["gamma0"], c_f64p), ptr(out["gamma_sums"], c_f64p),
                                            ptr(out["reduced"], c_f64p)), "fetch")
         return out
+
+    def set_statistics(self, xisum, gamma0, gamma_sums):
+        """Load per-contig statistics ([C,M,M], [C,M], [C,K,M]) instead of computing them (constructor pre-fill, checkpoint)."""
+        xisum = np.ascontiguousarray(xisum, np.float64); gamma0 = np.ascontiguousarray(gamma0, np.float64)
+        gamma_sums = np.ascontiguousarray(gamma_sums, np.float64)
+        M = gamma0.shape[1]
+        if xisum.shape != (self.C, M, M) or gamma_sums.shape != (self.C, self.K, M):
+            raise ValueError("set_statistics: expected xisum[C,M,M], gamma0[C,M], gamma_sums[C,K,M]")
+        self._check(lib().smcpp_b200_set_statistics(self._h, ctypes.c_int(M), ptr(xisum, c_f64p), ptr(gamma0, c_f64p),
+                                                    ptr(gamma_sums, c_f64p)), "set_statistics")
+        self.M = M
+
+    def q(self, pi, T, E, dpi=None, dT=None, dE=None):
+        """M-step objective from the resident statistics: q[4], and dq[4, D] when the derivative arrays dpi[D,M], dT[D,M,M],
+        dE[D,K,M] are given (reference InferenceManager::Q on autodiff scalars)."""
+        pi = np.ascontiguousarray(pi, np.float64); T = np.ascontiguousarray(T, np.float64); E = np.ascontiguousarray(E, np.float64)
+        M = pi.shape[0]
+        if T.shape != (M, M) or E.shape != (self.K, M):
+            raise ValueError("q: T must be [M,M], E must be [K,M]")
+        q = np.empty(4)
+        D = 0
+        dq = None
+        if dpi is not None:
+            dpi = np.ascontiguousarray(dpi, np.float64); dT = np.ascontiguousarray(dT, np.float64); dE = np.ascontiguousarray(dE, np.float64)
+            D = dpi.shape[0]
+            if dpi.shape != (D, M) or dT.shape != (D, M, M) or dE.shape != (D, self.K, M):
+                raise ValueError("q: derivative arrays must be dpi[D,M], dT[D,M,M], dE[D,K,M]")
+            dq = np.empty((4, D))
+        self._check(lib().smcpp_b200_q(self._h, ctypes.c_int(M), ptr(pi, c_f64p), ptr(T, c_f64p), ptr(E, c_f64p), ctypes.c_int(D),
+                                       ptr(dpi, c_f64p), ptr(dT, c_f64p), ptr(dE, c_f64p), ptr(q, c_f64p), ptr(dq, c_f64p)), "q")
+        return q if dq is None else (q, dq)
 
     def reduced_device_ptr(self):
         p = ctypes.c_void_p(); n = ctypes.c_int64()

@@ -159,6 +159,10 @@ struct smcpp_b200_ctx {
     std::vector<double> eig_store;  // library-computed eigensystems of the last estep
     std::vector<int32_t> eig_cplx;  // per eigen key: the spectrum had a complex pair (library-computed eigensystems)
     std::vector<int64_t> gcol_off;  // first posterior column of each contig (save_gamma)
+    DevBuf<double> q_in, q_terms, q_out;   // M-step objective (smcpp_b200_q)
+    DevBuf<uint8_t> d_present;
+    DevBuf<int32_t> d_key_nb;
+    bool stats_valid = false;       // the per-contig statistics on the device belong to a finished E-step (or set_statistics)
     bool pending = false;           // an E-step is enqueued and its boundary counters have not been looked at yet
 
     smcpp_b200_stats_t stats = {};
@@ -288,7 +292,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_pwq.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
+    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
     ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
@@ -482,7 +486,17 @@ int smcpp_b200_set_contigs(smcpp_b200_ctx *ctx, int n_contigs, const int32_t *co
     CU(ctx->d_key_of_eig.ensure(std::max(1, ctx->n_eig)));
     if (ctx->n_eig)
         CU(cudaMemcpy(ctx->d_key_of_eig.p, ctx->eig_keys.data(), ctx->n_eig * sizeof(int), cudaMemcpyHostToDevice));
+    {
+        std::vector<int32_t> nb(K, 0);
+        for (int k = 0; k < K; ++k)
+            for (int pp = 0; pp < npop; ++pp) nb[k] += ctx->keys[(size_t)k * Q + 3 * pp + 2];     // block_key::nb(), include/block_key.h:34-39
+        CU(ctx->d_key_nb.ensure(K));
+        CU(cudaMemcpy(ctx->d_key_nb.p, nb.data(), K * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(ctx->d_present.ensure((size_t)n_contigs * K));
+        CU(cudaMemcpy(ctx->d_present.p, ctx->present.data(), (size_t)n_contigs * K, cudaMemcpyHostToDevice));
+    }
     ctx->plan_valid = false;
+    ctx->stats_valid = false;
     ctx->M = 0;
     ctx->contigs_ok = true;
     return 0;
@@ -1003,6 +1017,7 @@ static int complete_estep(smcpp_b200_ctx *ctx, F refetch)
             ctx->burn_in_fwd_adapt += std::max(ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt, 256);
         }
     }
+    ctx->stats_valid = !gave_up;
     ctx->stats.fwd_sweeps = fwd_sweeps;
     ctx->stats.bwd_sweeps = bwd_sweeps;
     ctx->stats.fwd_redone = fwd_redone;
@@ -1144,6 +1159,63 @@ int smcpp_b200_estep_device(smcpp_b200_ctx *ctx, int M, const double *pi, const 
     if (run_estep(ctx, M, pi, T, E, n_eig, P, Pinv, d, d_scaled, scale, upload_inputs != 0)) return 1;
     if (complete_estep(ctx, []() { return 0; })) return 1;
     return finish_timing(ctx);
+}
+
+int smcpp_b200_set_statistics(smcpp_b200_ctx *ctx, int M, const double *xisum, const double *gamma0, const double *gamma_sums)
+{
+    if (!ctx || !xisum || !gamma0 || !gamma_sums) return 1;
+    if (ctx->C == 0 || !ctx->contigs_ok) return fail(ctx, "set_statistics: set_contigs() has not been called (or failed)");
+    if (M < 1 || M > kMaxMp) return fail(ctx, "set_statistics: M must be in [1, 128]");
+    DeviceGuard guard(ctx->device);
+    if (complete_estep(ctx, []() { return 0; })) return 1;
+    if (make_plan(ctx, M)) return 1;
+    const size_t C = ctx->C, K = ctx->K;
+    CU(cudaMemcpyAsync(ctx->o_xisum.p, xisum, C * M * M * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->o_gamma0.p, gamma0, C * M * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->o_gamma_sums.p, gamma_sums, C * K * M * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->stats_valid = true;
+    return 0;
+}
+
+int smcpp_b200_q(smcpp_b200_ctx *ctx, int M, const double *pi, const double *T, const double *E, int n_deriv, const double *dpi,
+                 const double *dT, const double *dE, double *q, double *dq)
+{
+    if (!ctx || !pi || !T || !E || !q) return 1;
+    if (n_deriv < 0 || (n_deriv > 0 && (!dpi || !dT || !dE || !dq))) return fail(ctx, "q: derivative arrays missing");
+    DeviceGuard guard(ctx->device);
+    if (complete_estep(ctx, []() { return 0; })) return 1;
+    if (!ctx->stats_valid || !ctx->plan_valid || ctx->M != M)
+        return fail(ctx, "q: no statistics for this M on the device (run estep() or set_statistics() first)");
+    const size_t C = ctx->C, K = ctx->K, D = n_deriv, MM = (size_t)M * M;
+    const size_t n_val = M + MM + K * M, n_in = n_val * (1 + D), n_q = 4 * (1 + D);
+    CU(ctx->q_in.ensure(n_in));
+    CU(ctx->q_terms.ensure(C * n_q));
+    CU(ctx->q_out.ensure(n_q));
+    CU(ctx->h_in.ensure(std::max(n_in, ctx->h_in.n)));
+    double *h = ctx->h_in.p;
+    std::memcpy(h, pi, M * sizeof(double));
+    std::memcpy(h + M, T, MM * sizeof(double));
+    std::memcpy(h + M + MM, E, K * M * sizeof(double));
+    double *hd = h + n_val;                       // [dpi (D x M) | dT (D x M x M) | dE (D x K x M)]
+    if (D) {
+        std::memcpy(hd, dpi, D * M * sizeof(double));
+        std::memcpy(hd + D * M, dT, D * MM * sizeof(double));
+        std::memcpy(hd + D * M + D * MM, dE, D * K * M * sizeof(double));
+    }
+    CU(cudaMemcpyAsync(ctx->q_in.p, h, n_in * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    const double *d = ctx->q_in.p, *dd = d + n_val;
+    launch_q((int)C, M, (int)K, (int)D, d, d + M, d + M + MM, dd, dd + D * M, dd + D * M + D * MM, ctx->d_present.p, ctx->d_key_nb.p,
+             ctx->o_gamma0.p, ctx->o_xisum.p, ctx->o_gamma_sums.p, ctx->q_terms.p, ctx->q_out.p, ctx->st);
+    std::vector<double> out(n_q);
+    CU(cudaMemcpyAsync(out.data(), ctx->q_out.p, n_q * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    for (int t = 0; t < 4; ++t) {
+        q[t] = out[(size_t)t * (1 + D)];
+        for (size_t p = 0; p < D; ++p) dq[(size_t)t * D + p] = out[(size_t)t * (1 + D) + 1 + p];
+    }
+    return 0;
 }
 
 int smcpp_b200_reduced_device_ptr(smcpp_b200_ctx *ctx, void **ptr, int64_t *count)

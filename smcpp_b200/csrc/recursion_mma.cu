@@ -31,7 +31,7 @@ namespace smcb {
 constexpr int kMW = 4;             // warps per CTA
 constexpr unsigned kAll = 0xffffffffu;
 #ifndef SMCB_STREAM_PW
-#define SMCB_STREAM_PW 1
+#define SMCB_STREAM_PW 0
 #endif
 constexpr bool kStreamPw = SMCB_STREAM_PW != 0;   // d~^span rows: ld.global.nc.L1::no_allocate
 

@@ -81,30 +81,44 @@ class InferenceManager:
         self.set_hmm_inputs(mi["pi"], mi["T"], mi["E"])
         return mi
 
-    def Q(self):
-        """Value parts of InferenceManager::Q() (reference src/inference_manager.cpp:116-126, src/hmm.cpp:155-193):
-        [sum log(pi) gamma0, sum_{nb=0 keys} log(e) gamma_sums, sum_{nb>0 keys} ..., sum log(T) xisum], summed over
-        contigs.  Before the first E-step the reference's HMM constructor has pre-filled gamma_sums with span * pi
-        (src/hmm.cpp:18-26) and zeroed the rest; so do we."""
+    def Q(self, dpi=None, dT=None, dE=None):
+        """InferenceManager::Q() (reference src/inference_manager.cpp:116-126, src/hmm.cpp:155-193) on the device
+        (smcpp_b200_q): [sum log(pi) gamma0, sum_{nb=0 keys} log(e) gamma_sums, sum_{nb>0 keys} ..., sum log(T) xisum], per contig
+        in the reference's order with its doubly compensated summation, keys present in the contig only, summed over
+        contigs (and over this process's devices).  A present key with a non-positive emission entry makes its class
+        -inf (the reference warns there).  With the derivative arrays dpi[D,M], dT[D,M,M], dE[D,K,M] of the current
+        inputs the gradient dq[4,D] is returned as well (the reference evaluates Q on autodiff scalars).
+
+        Before the first E-step the reference's HMM constructor has pre-filled gamma_sums with span * pi
+        (src/hmm.cpp:16-27) and zeroed the rest; so do we (set_statistics)."""
         if self._inputs is None:
             raise RuntimeError("Q: set_hmm_inputs() / set_model() has not been called")
         pi, T, E, _ = self._inputs
         if self._out is None:
-            gs = np.zeros((self.K, self.M))
             lut = {tuple(int(v) for v in k): i for i, k in enumerate(self.keys)}
-            for ob in self._obs:
-                uniq, inv = np.unique(ob[:, 1:], axis=0, return_inverse=True)
-                tot = np.bincount(inv.reshape(-1), weights=ob[:, 0].astype(np.float64), minlength=len(uniq))
-                for u, t in zip(uniq, tot):
-                    gs[lut[tuple(int(v) for v in u)]] += t * pi
-            g0 = np.zeros(self.M)
-            xi = np.zeros((self.M, self.M))
-        else:
-            r = parallel.unpack_reduced(self._out["reduced"], self.M, self.K)
-            gs, g0, xi = r["gamma_sums"], r["gamma0"], r["xisum"]
-        nb = self.keys[:, 2::3].sum(axis=1)
-        le = np.log(E) * gs
-        return np.array([np.dot(np.log(pi), g0), le[nb == 0].sum(), le[nb > 0].sum(), (np.log(T) * xi).sum()])
+            for ctx, idx in zip(self._ctx, self._shards):
+                if ctx is None:
+                    continue
+                gs = np.zeros((len(idx), self.K, self.M))
+                for local, glob in enumerate(idx):
+                    ob = self._obs[glob]
+                    uniq, inv = np.unique(ob[:, 1:], axis=0, return_inverse=True)
+                    tot = np.bincount(inv.reshape(-1), weights=ob[:, 0].astype(np.float64), minlength=len(uniq))
+                    for u, t in zip(uniq, tot):
+                        gs[local, lut[tuple(int(v) for v in u)]] += t * pi
+                ctx.set_statistics(np.zeros((len(idx), self.M, self.M)), np.zeros((len(idx), self.M)), gs)
+        q = np.zeros(4)
+        dq = None
+        for ctx in self._ctx:
+            if ctx is None:
+                continue
+            r = ctx.q(pi, T, E, dpi, dT, dE)
+            if dpi is None:
+                q += r
+            else:
+                q += r[0]
+                dq = r[1] if dq is None else dq + r[1]
+        return q if dpi is None else (q, dq)
 
     def set_option(self, name, value):
         for c in self._ctx:

@@ -63,19 +63,3 @@ def test_polarization_error_folds_keys():
     k1, k2 = keys.index((0, 1, 4)), keys.index((2, 3, 4))                      # folded partners: a -> 2-a, b -> nb-b
     assert not np.allclose(a[k1], a[k2])
     assert np.allclose(b[k1], b[k2], rtol=1e-12)
-
-
-def test_q_of_host_mirror_matches_reference_values():
-    # Q is computed by the host mirror from the E-step outputs; feed it the reference's own outputs here
-    from smcpp_b200 import parallel
-    from smcpp_b200.inference import InferenceManager
-    g = Golden("c4_twopop_1200")
-    im = InferenceManager.__new__(InferenceManager)   # no GPU in this test: fill the fields Q() reads
-    im.M, im.K, im.keys = g.M, g.ref["keys"].shape[0], g.ref["keys"]
-    im._obs = g.contigs
-    im._inputs = (g.ref["pi"], g.ref["T"], g.ref["E"], None)
-    im._out = {"reduced": parallel.pack_reduced(g.ref["ll"], g.ref["gamma0"], g.ref["xisum"], g.ref["gamma_sums"])}
-    assert np.allclose(im.Q(), g.ref["Q"], rtol=1e-10)
-    im._out = None   # before any E-step: the constructor's span * pi prefill (reference src/hmm.cpp:18-26)
-    q = im.Q()
-    assert q[0] == 0 and q[3] == 0 and q[1] < 0 and q[2] < 0
