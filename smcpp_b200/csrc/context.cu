@@ -158,6 +158,10 @@ struct smcpp_b200_ctx {
     PinBuf<double> h_out;
     std::vector<double> eig_store;  // library-computed eigensystems of the last estep
     std::vector<int32_t> eig_cplx;  // per eigen key: the spectrum had a complex pair (library-computed eigensystems)
+    std::vector<uint8_t> irregular; // per eigen key: complex pair (P_r Pinv_r != I) or a negative eigenvalue -> literal formulas
+    bool literal_mode = false, plan_literal = false;
+    DevBuf<uint8_t> m_irregular;
+    DevBuf<double> w_Xlit, w_gslit, w_lit_scratch;
     std::vector<int64_t> gcol_off;  // first posterior column of each contig (save_gamma)
     DevBuf<double> q_in, q_terms, q_out;   // M-step objective (smcpp_b200_q)
     DevBuf<uint8_t> d_present;
@@ -181,6 +185,7 @@ struct smcpp_b200_ctx {
         m.c_negzero2 = 0x8000000080000000ull; m.c_one2 = 0x3f8000003f800000ull;
         for (int i = 0; i < 4; ++i) m.hot_keys[i] = hot_keys[i];
         m.pwtab = m_pwtab.p; m.span_list = d_span_list.p; m.n_span = (int)span_list.size(); m.invdiff = m_invdiff.p;
+        m.irregular = literal_mode ? m_irregular.p : nullptr; m.literal = literal_mode ? 1 : 0;
         return m;
     }
     Plan plan() const
@@ -208,6 +213,7 @@ struct smcpp_b200_ctx {
         w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p; w.fwd_rerun = w_fwd_rerun.p;
         w.counters = w_counters.p;
         w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p; w.sums = w_sums.p;
+        w.Xlit = w_Xlit.p; w.gslit = w_gslit.p; w.lit_scratch = w_lit_scratch.p;
         w.ll = o_ll.p; w.xisum = o_xisum.p; w.gamma0 = o_gamma0.p; w.gamma_sums = o_gamma_sums.p; w.reduced = o_reduced.p;
         return w;
     }
@@ -292,7 +298,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_pwq.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
+    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->m_irregular.release(); ctx->w_Xlit.release(); ctx->w_gslit.release(); ctx->w_lit_scratch.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
     ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
@@ -535,7 +541,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     int64_t maxL = 0;
     for (int c = 0; c < ctx->C; ++c) maxL = std::max<int64_t>(maxL, ctx->blk_off[c + 1] - ctx->blk_off[c]);
     int Lc;
-    if (ctx->opt_force_sequential) Lc = (int)maxL;
+    if (ctx->opt_force_sequential || ctx->literal_mode) Lc = (int)maxL;
     else if (ctx->opt_chunk_blocks > 0) Lc = ctx->opt_chunk_blocks;
     else {
         // as many chunks as fit in ONE resident wave of the recursion kernels (a partial second wave would
@@ -598,7 +604,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         const int64_t per = ctx->total / ((int64_t)ctx->n_sm * 8);
         slab = (int)std::min<int64_t>(16384, std::max<int64_t>(2048, (per / 32) * 32));
     }
-    const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M;
+    const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M && ctx->plan_literal == ctx->literal_mode;
     ctx->plan_burn = burn;
     if (same) return 0;
     ctx->plan_valid = false;   // a failure below must not leave the previous plan looking current
@@ -713,6 +719,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     ctx->n_cols = cols;
     ctx->plan_Lc = Lc;
     ctx->plan_slab = slab;
+    ctx->plan_literal = ctx->literal_mode;
     ctx->M = M;
     ctx->Mp = Mp;
 #define UP(buf, vec)                                                                                             \
@@ -787,6 +794,11 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->w_fwd_rerun.ensure(ctx->n_chunks));
     CU(ctx->w_counters.ensure(8));
     CU(ctx->h_counters.ensure(8));
+    if (ctx->literal_mode) {
+        CU(ctx->w_Xlit.ensure((size_t)ctx->n_slabs * MM));
+        CU(ctx->w_gslit.ensure((size_t)ctx->n_slabs * NE * Mp));
+        CU(ctx->w_lit_scratch.ensure((size_t)ctx->n_slabs * 2 * MM));
+    }
     CU(ctx->w_Xpart.ensure((size_t)ctx->n_slabs * MM));
     CU(ctx->w_Rpart.ensure((size_t)ctx->n_slabs * NE * MM));
     CU(ctx->w_dpart.ensure((size_t)ctx->n_slabs * NE * Mp));
@@ -815,7 +827,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
 static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, const Plan &p, const Work &w)
 {
     cudaEventRecord(ctx->ev[2], ctx->st);
-    const bool split = ctx->opt_stats_streams == 2 && (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0;
+    const bool split = ctx->opt_stats_streams == 2 && !m.literal && (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0;
     if (split) {
         // the span-1 and the span>1 statistics kernels are independent: side by side on two streams
         cudaEventRecord(ctx->ev_setup_done, ctx->st);
@@ -826,6 +838,7 @@ static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, cons
     } else {
         launch_stats(m, p, w, ctx->st, ctx->st);
     }
+    if (m.literal) { launch_stats_literal(m, p, w, ctx->st); ctx->stats.kernel_launches += 1; }
     cudaEventRecord(ctx->ev[3], ctx->st);
     ctx->stats.kernel_launches += ((m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_items > 0) ? 2 : 1;
     ctx->gamma_valid = false;
@@ -848,9 +861,52 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     if (ctx->C == 0 || !ctx->contigs_ok) return fail(ctx, "estep: set_contigs() has not been called (or failed)");
     if (M < 1 || M > kMaxMp) return fail(ctx, "estep: M must be in [1, 128]");
     DeviceGuard guard(ctx->device);
-    if (make_plan(ctx, M)) return 1;
     const int K = ctx->K, NE = ctx->n_eig;
     ctx->pending = false;
+    if (upload) {
+        if (!pi || !T || !E) return fail(ctx, "estep: pi, T and E are required");
+        ctx->eig_cplx.assign(std::max(1, NE), 0);
+        if (!P) {
+            // library-side eigensystems (host QR algorithm), same routine as smcpp_b200_eigensystems()
+            ctx->eig_store.resize((size_t)NE * (2 * (size_t)M * M + 2 * M + 1));
+            double *eP = ctx->eig_store.data(), *ePi = eP + (size_t)NE * M * M, *ed = ePi + (size_t)NE * M * M,
+                   *eds = ed + (size_t)NE * M, *esc = eds + (size_t)NE * M;
+            std::string msg;
+            if (smcb::host_eigensystems(M, K, NE, ctx->eig_keys.data(), T, E, eP, ePi, ed, eds, esc, ctx->eig_cplx.data(), &msg))
+                return fail(ctx, "estep: eigensystems: " + msg);
+            P = eP; Pinv = ePi; d = ed; dsc = eds; scale = esc;
+        } else if (n_eig != NE) {
+            return fail(ctx, "estep: n_eig does not match the number of keys that occur with span > 1");
+        } else {
+            // eigensystems handed in by the caller: a complex pair shows as P_r Pinv_r != I (only the real parts were kept,
+            // reference include/transition_bundle.h:19-24)
+            for (int e = 0; e < NE; ++e) {
+                const double *Pe = P + (size_t)e * M * M, *Pie = Pinv + (size_t)e * M * M;
+                double worst = 0.0;
+                for (int i = 0; i < M && worst <= 1e-8; ++i)
+                    for (int j = 0; j < M; ++j) {
+                        double acc = 0.0;
+                        for (int a = 0; a < M; ++a) acc += Pe[(size_t)i * M + a] * Pie[(size_t)a * M + j];
+                        worst = std::max(worst, std::fabs(acc - (i == j ? 1.0 : 0.0)));
+                    }
+                ctx->eig_cplx[e] = worst > 1e-8 || !(worst == worst);
+            }
+        }
+        // irregular spectra take the reference's literal formulas: complex pairs, negative (or NaN) eigenvalues
+        ctx->irregular.assign(std::max(1, NE), 0);
+        bool any = false;
+        for (int e = 0; e < NE; ++e) {
+            bool bad = ctx->eig_cplx[e] != 0;
+            for (int a = 0; a < M; ++a) bad = bad || !(dsc[(size_t)e * M + a] >= 0.0);
+            ctx->irregular[e] = bad;
+            any = any || bad;
+        }
+        ctx->literal_mode = any;
+        ctx->stats.literal_keys = 0;
+        for (int e = 0; e < NE; ++e) ctx->stats.literal_keys += ctx->irregular[e];
+    }
+    if (make_plan(ctx, M)) return 1;
+    if (ctx->save_gamma && ctx->literal_mode) return fail(ctx, "estep: save_gamma is not available for irregular (complex / negative) spectra");
     if (ctx->save_gamma) {
         ctx->gcol_off.assign(ctx->C + 1, 0);     // member: the asynchronous copy below reads it after this function returns
         for (int c = 0; c < ctx->C; ++c) ctx->gcol_off[c + 1] = ctx->gcol_off[c] + (ctx->blk_off[c + 1] - ctx->blk_off[c]) + 1;
@@ -860,19 +916,9 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
         CU(cudaMemcpyAsync(ctx->d_gcol_off.p, ctx->gcol_off.data(), (ctx->C + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     }
     if (upload) {
-        if (!pi || !T || !E) return fail(ctx, "estep: pi, T and E are required");
-        if (!P) {
-            // library-side eigensystems (host QR algorithm), same routine as smcpp_b200_eigensystems()
-            ctx->eig_store.resize((size_t)NE * (2 * (size_t)M * M + 2 * M + 1));
-            double *eP = ctx->eig_store.data(), *ePi = eP + (size_t)NE * M * M, *ed = ePi + (size_t)NE * M * M,
-                   *eds = ed + (size_t)NE * M, *esc = eds + (size_t)NE * M;
-            ctx->eig_cplx.assign(std::max(1, NE), 0);
-            std::string msg;
-            if (smcb::host_eigensystems(M, K, NE, ctx->eig_keys.data(), T, E, eP, ePi, ed, eds, esc, ctx->eig_cplx.data(), &msg))
-                return fail(ctx, "estep: eigensystems: " + msg);
-            P = eP; Pinv = ePi; d = ed; dsc = eds; scale = esc;
-        } else if (n_eig != NE) {
-            return fail(ctx, "estep: n_eig does not match the number of keys that occur with span > 1");
+        if (ctx->literal_mode) {
+            CU(ctx->m_irregular.ensure(std::max(1, NE)));
+            CU(cudaMemcpyAsync(ctx->m_irregular.p, ctx->irregular.data(), std::max(1, NE), cudaMemcpyHostToDevice, ctx->st));
         }
         double *h = ctx->h_in.p;
         size_t o = 0;
@@ -903,7 +949,7 @@ static int run_estep(smcpp_b200_ctx *ctx, int M, const double *pi, const double 
     cudaEventRecord(ctx->ev[1], ctx->st);
     CU(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), ctx->st));
     CU(cudaMemsetAsync(w.fwd_rerun, 0, p.n_chunks, ctx->st));
-    const bool mma = (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential;
+    const bool mma = (m.Mp == 32 || m.Mp == 64 || m.Mp == 128) && p.n_chunks >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential && !ctx->literal_mode;
     ctx->use_mma = mma;
     const bool fwd_mma = mma && (ctx->opt_force_mma_forward || mma_forward_pays(p.n_chunks, ctx->n_sm, m.Mp, ctx->rec));
     const bool tiles = fwd_mma && m.Mp == 32 && ctx->rec.tiles == 2;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
 #pragma unroll
                 for (int r = 0; r < R; ++r) u[r] = fma(__ldg(PinvT + (size_t)i * Mp + lane + 32 * r), xi, u[r]);
             }
-            if ((Mp == 64 || Mp == 128) && b >= s) {   // operand of the tiled statistics kernels (stats32.cu: k_statsTe); Mp = 96 stays generic
+            if ((Mp == 64 || Mp == 128) && b >= s && !m.literal) {   // operand of the tiled statistics kernels (stats32.cu: k_statsTe); Mp = 96 stays generic
 #pragma unroll
                 for (int r = 0; r < R; ++r) w.uvec[(size_t)(g0 + b) * Mp + lane + 32 * r] = u[r];
             }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_forward(Model m, Plan p, Wor
 
 void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
 {
-    if (m.Mp == 32) { launch_forward32(m, p, w, pass, st); return; }
+    if (m.Mp == 32 && !m.literal) { launch_forward32(m, p, w, pass, st); return; }
     const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
     const size_t smem = (size_t)kSeqWarps * m.Mp * (sizeof(double) + sizeof(float));
     switch (m.Mp / 32) {
@@ -343,6 +343,17 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
                 for (int r = 0; r < R; ++r) nb[r] = fma(__ldg(m.TdT + (size_t)j * Mp + lane + 32 * r), tj, nb[r]);
             }
         }
+        if (m.literal && e >= 0) {
+            // the reference takes log() of the new vector (src/hmm.cpp:123-127): a negative entry becomes NaN and the
+            // following normalisation spreads it over the whole vector
+            bool neg = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) neg = neg || nb[r] < 0.0;
+            if (__any_sync(0xffffffffu, neg)) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) nb[r] = nan("");
+            }
+        }
         double part = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) part += nb[r];
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) k_backward(Model m, Plan p, Wo
 
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st)
 {
-    if (m.Mp == 32) { launch_backward32(m, p, w, pass, st); return; }
+    if (m.Mp == 32 && !m.literal) { launch_backward32(m, p, w, pass, st); return; }
     const int blocks = (p.n_chunks + kSeqWarps - 1) / kSeqWarps;
     const size_t smem = (size_t)kSeqWarps * m.Mp * sizeof(double);
     switch (m.Mp / 32) {
@@ -519,6 +530,7 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
     // ---------------- span>1 blocks, one pass per eigen key present in the slab
     for (int e = 0; e < m.n_eig; ++e) {
         if (!mask_bit(mask, 1 + e)) continue;
+        if (m.irregular && m.irregular[e]) continue;      // literal formulas: k_stats_literal
         double acc[TM][TM];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -611,8 +623,8 @@ __global__ void __launch_bounds__(kStatThreads) k_stats(Model m, Plan p, Work w)
 
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs)
 {
-    if (m.Mp == 32) { launch_stats32(m, p, w, st, st_runs); return; }
-    if (m.Mp == 64 || m.Mp == 128) { launch_stats64(m, p, w, st, st_runs); return; }
+    if (m.Mp == 32 && !m.literal) { launch_stats32(m, p, w, st, st_runs); return; }
+    if ((m.Mp == 64 || m.Mp == 128) && !m.literal) { launch_stats64(m, p, w, st, st_runs); return; }
     const int smem = stats_smem_bytes(m);
     // cudaFuncSetAttribute is a host-side call that costs ~1 ms: do it once per (instantiation, size)
     static std::atomic<size_t> configured[5][kMaxDevices];
@@ -660,7 +672,7 @@ __global__ void __launch_bounds__(256) k_reduce_partials(Model m, Plan p, Work w
     else if (x < oG) { const size_t y = x - oD; src = w.dpart + y; sstride = (size_t)NE * Mp; bit = 1 + (int)(y / Mp); }
     else { src = w.gspart + (x - oG); sstride = (size_t)K * Mp; bit = 0; }
     double acc = 0.0;
-    if ((Mp == 32 || Mp == 64 || Mp == 128) && x >= oR && x < oG) {
+    if ((Mp == 32 || Mp == 64 || Mp == 128) && !m.literal && x >= oR && x < oG) {
         // M <= 64: R_e / D_e partials come per work item of k_stats32e / k_stats64e (fixed order: bitwise reproducible)
         const bool isR = x < oD;
         const size_t y = isR ? x - oR : x - oD;
@@ -695,6 +707,22 @@ __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
     __syncthreads();
     for (int e = 0; e < NE; ++e) {
         if (!mask_bit(mask, 1 + e)) continue;
+        if (m.irregular && m.irregular[e]) {
+            // literal path: the per-slab partials are already in state space (xis and v of src/hmm.cpp:116-122)
+            const int ke = m.key_of_eig[e];
+            for (size_t x = tid; x < MM; x += nth) {
+                double acc = 0.0;
+                for (int sl = p.slab_off[t]; sl < p.slab_off[t + 1]; ++sl) acc += w.Xlit[(size_t)sl * MM + x];
+                X[x] += acc;
+            }
+            for (int i = tid; i < M; i += nth) {
+                double acc = 0.0;
+                for (int sl = p.slab_off[t]; sl < p.slab_off[t + 1]; ++sl) acc += w.gslit[((size_t)sl * NE + e) * Mp + i];
+                gso[(size_t)ke * M + i] += acc;
+            }
+            __syncthreads();
+            continue;
+        }
         const double *dsc = m.dsc + (size_t)e * Mp, *dr = m.dr + (size_t)e * Mp;
         const double *P = m.P + (size_t)e * Mp * Mp, *Pinv = m.Pinv + (size_t)e * Mp * Mp;
         const double *R = S + oR + (size_t)e * MM, *D = S + oD + (size_t)e * Mp;
@@ -778,6 +806,105 @@ void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t 
     k_finalize<<<p.n_contigs, 256, 0, st>>>(m, p, w);
     const long n = 1 + m.M + (long)m.M * m.M + (long)m.K * m.M;
     k_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(m, p, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// literal statistics of span>1 blocks whose eigen key is irregular: the reference's per-block formulas
+// (src/hmm.cpp:113-122) with its span table (src/transition_bundle.cpp:36-53), including the element-wise
+// abs() and whatever NaN the table holds.  One CTA per slab, one block at a time, three M^3 stages:
+//   S(a,b) = u_a w_b sq(a,b)        u = Pinv_r alpha_{l-1},  w = P_r^T beta_l (stored by the backward pass)
+//   Z      = S Pinv_r
+//   dg_i   = sum_a P_r(i,a) d_a Z(a,i) ;  Y = P_r Z ;  xis = |Y diag(e)| span / sum|dg| ;  v = span |dg| / sum|dg|
+// (the reference goes through log/exp of these; the common factors exp(-log_c + log_p) cancel).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double span_table_entry(double da, double db, int a, int b, int span)
+{
+    if (a == b) return pow(da, (double)(span - 1)) * (double)span;
+    double d1 = da, d2 = db;
+    if (fabs(d1) < fabs(d2)) { const double t = d1; d1 = d2; d2 = t; }
+    return exp((double)span * log(d1) + log1p(-pow(d2 / d1, (double)span))) / (d1 - d2);
+}
+
+__global__ void __launch_bounds__(256) k_stats_literal(Model m, Plan p, Work w)
+{
+    const int M = m.M, Mp = m.Mp, NE = m.n_eig;
+    const size_t MM = (size_t)Mp * Mp;
+    const int slab = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const int t = p.sl_contig[slab];
+    const uint32_t *mask = p.sl_mask + (size_t)slab * p.mask_words;
+    const int64_t g0 = p.blk_off[t];
+    const int2 *rec = p.srec + g0 + p.sl_start[slab];
+    const int32_t *seg = p.seg + (size_t)slab * (NE + 2);
+    double *Xl = w.Xlit + (size_t)slab * MM;
+    double *S = w.lit_scratch + (size_t)slab * 2 * MM, *Z = S + MM;
+    __shared__ double u_s[kMaxMp], w_s[kMaxMp], dg_s[kMaxMp], red_s[256];
+    const int Lc = p.chunk_blocks;
+    const int64_t colbase = p.col_off[t];
+    for (size_t x = tid; x < MM; x += nth) Xl[x] = 0.0;
+    for (int x = tid; x < NE * Mp; x += nth) w.gslit[(size_t)slab * NE * Mp + x] = 0.0;
+    __syncthreads();
+    for (int e = 0; e < NE; ++e) {
+        if (!m.irregular[e] || !mask_bit(mask, 1 + e)) continue;
+        const double *P = m.P + (size_t)e * MM, *Pinv = m.Pinv + (size_t)e * MM;
+        const double *dsc = m.dsc + (size_t)e * Mp, *dr = m.dr + (size_t)e * Mp;
+        const double *ek = m.E + (size_t)m.key_of_eig[e] * Mp;
+        double *gsl = w.gslit + ((size_t)slab * NE + e) * Mp;
+        for (int it = seg[1 + e]; it < seg[2 + e]; ++it) {
+            const int bi = rec[it].x, span = m.span_list[rec[it].y];
+            const int cb = bi / Lc;
+            const float *ap = w.alpha + (colbase + (int64_t)cb * (Lc + 1) + (bi - cb * Lc)) * Mp;
+            const double *bv = w.bvec + (size_t)(g0 + bi) * Mp;
+            if (tid < M) {
+                double acc = 0.0;
+                for (int i = 0; i < M; ++i) acc += Pinv[(size_t)tid * Mp + i] * (double)ap[i];
+                u_s[tid] = acc;
+                w_s[tid] = bv[tid];
+            }
+            __syncthreads();
+            for (size_t x = tid; x < MM; x += nth) {
+                const int a = (int)(x / Mp), b = (int)(x % Mp);
+                S[x] = (a < M && b < M) ? u_s[a] * w_s[b] * span_table_entry(dsc[a], dsc[b], a, b, span) : 0.0;
+            }
+            __syncthreads();
+            for (size_t x = tid; x < MM; x += nth) {
+                const int a = (int)(x / Mp), i = (int)(x % Mp);
+                double acc = 0.0;
+                if (a < M && i < M)
+                    for (int b = 0; b < M; ++b) acc += S[(size_t)a * Mp + b] * Pinv[(size_t)b * Mp + i];
+                Z[x] = acc;
+            }
+            __syncthreads();
+            if (tid < M) {
+                double acc = 0.0;
+                for (int a = 0; a < M; ++a) acc += P[(size_t)tid * Mp + a] * dr[a] * Z[(size_t)a * Mp + tid];
+                dg_s[tid] = fabs(acc);
+            }
+            __syncthreads();
+            red_s[tid] = 0.0;
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int i = 0; i < M; ++i) sum += dg_s[i];
+                red_s[0] = (double)span / sum;
+            }
+            __syncthreads();
+            const double C = red_s[0];
+            if (tid < M) gsl[tid] += dg_s[tid] * C;
+            for (size_t x = tid; x < MM; x += nth) {
+                const int i = (int)(x / Mp), j = (int)(x % Mp);
+                if (i < M && j < M) {
+                    double acc = 0.0;
+                    for (int a = 0; a < M; ++a) acc += P[(size_t)i * Mp + a] * Z[(size_t)a * Mp + j];
+                    Xl[x] += fabs(acc * ek[j]) * C;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+void launch_stats_literal(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
+{
+    k_stats_literal<<<p.n_slabs, 256, 0, st>>>(m, p, w);
 }
 
 // d~^span for every (eigen key, distinct span): Model::pwtab

@@ -60,6 +60,11 @@ struct Model {
     const int32_t *span_list;// [n_span] distinct spans > 1 of the data set
     int n_span;
     const double *invdiff;   // [n_eig][Mp][Mp] 1/(d~_a - d~_b), built only for posterior decoding
+    // Irregular spectra (the reference keeps only the real parts of a complex eigensystem, include/transition_bundle.h:19-24,
+    // so P_r Pinv_r != I; a negative eigenvalue makes its span tables NaN, src/transition_bundle.cpp:46-50): such eigen
+    // keys take the reference's literal per-block formulas (k_stats_literal) instead of the O(M^2) displacement form.
+    const uint8_t *irregular;  // [n_eig] or nullptr
+    int literal;               // 1: some key is irregular -- sequential chains, generic kernels, NaN semantics of src/hmm.cpp:123-127
 };
 
 // Static per-dataset layout (set_contigs) + per-plan chunking.
@@ -130,6 +135,9 @@ struct Work {
     double *gspart;          // [n_slabs][K][Mp]
     double *scratch;         // [C][2][Mp*Mp]  temporaries of k_finalize
     double *sums;            // [C][sum_stride] slab partials reduced per contig: X | R_e | D_e | gs
+    double *Xlit;            // [n_slabs][Mp*Mp]       literal-path partials of X (irregular eigen keys only; else nullptr)
+    double *gslit;           // [n_slabs][n_eig][Mp]   literal-path partials of the gamma sums of the eigen keys
+    double *lit_scratch;     // [n_slabs][2][Mp*Mp]
     // outputs (device)
     double *ll;              // [C]
     double *xisum;           // [C][M][M]
@@ -173,6 +181,7 @@ void launch_check_backward(const Model &m, const Plan &p, const Work &w, double 
 // st_runs: stream of the span>1 statistics kernel (independent of the span-1 kernel; == st runs them back to back)
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
+void launch_stats_literal(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
