@@ -162,6 +162,8 @@ struct smcpp_b200_ctx {
     bool literal_mode = false, plan_literal = false;
     DevBuf<uint8_t> m_irregular;
     DevBuf<double> w_Xlit, w_gslit, w_lit_scratch;
+    DevBuf<int> w_nanpos;
+    DevBuf<uint8_t> w_poison;
     std::vector<int64_t> gcol_off;  // first posterior column of each contig (save_gamma)
     DevBuf<double> q_in, q_terms, q_out;   // M-step objective (smcpp_b200_q)
     DevBuf<uint8_t> d_present;
@@ -213,7 +215,7 @@ struct smcpp_b200_ctx {
         w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p; w.fwd_rerun = w_fwd_rerun.p;
         w.counters = w_counters.p;
         w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p; w.sums = w_sums.p;
-        w.Xlit = w_Xlit.p; w.gslit = w_gslit.p; w.lit_scratch = w_lit_scratch.p;
+        w.Xlit = w_Xlit.p; w.gslit = w_gslit.p; w.lit_scratch = w_lit_scratch.p; w.nanpos = w_nanpos.p; w.poison = w_poison.p;
         w.ll = o_ll.p; w.xisum = o_xisum.p; w.gamma0 = o_gamma0.p; w.gamma_sums = o_gamma_sums.p; w.reduced = o_reduced.p;
         return w;
     }
@@ -298,7 +300,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_span.release(); ctx->d_key.release(); ctx->d_span_id.release(); ctx->d_span_list.release(); ctx->m_pwtab.release(); ctx->m_pwq.release(); ctx->m_invdiff.release(); ctx->w_gamma.release(); ctx->d_gcol_off.release(); ctx->d_blk_off.release(); ctx->d_col_off.release();
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
-    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->m_irregular.release(); ctx->w_Xlit.release(); ctx->w_gslit.release(); ctx->w_lit_scratch.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
+    ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->m_irregular.release(); ctx->w_nanpos.release(); ctx->w_poison.release(); ctx->w_Xlit.release(); ctx->w_gslit.release(); ctx->w_lit_scratch.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
     ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
@@ -798,6 +800,8 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         CU(ctx->w_Xlit.ensure((size_t)ctx->n_slabs * MM));
         CU(ctx->w_gslit.ensure((size_t)ctx->n_slabs * NE * Mp));
         CU(ctx->w_lit_scratch.ensure((size_t)ctx->n_slabs * 2 * MM));
+        CU(ctx->w_nanpos.ensure(C));
+        CU(ctx->w_poison.ensure((size_t)C * ctx->K));
     }
     CU(ctx->w_Xpart.ensure((size_t)ctx->n_slabs * MM));
     CU(ctx->w_Rpart.ensure((size_t)ctx->n_slabs * NE * MM));

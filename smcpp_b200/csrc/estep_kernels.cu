@@ -761,16 +761,22 @@ __global__ void __launch_bounds__(256) k_finalize(Model m, Plan p, Work w)
         __syncthreads();
     }
     // xisum = max(X o Td, 1e-20); src/hmm.cpp:151-152
+    const bool nan_tail = m.literal && w.nanpos[t] >= 0;      // beta is NaN from that block down to the start of the contig
     double *xo = w.xisum + (size_t)t * M * M;
     for (int x = tid; x < M * M; x += nth) {
         const int i = x / M, j = x % M;
         const double v = X[(size_t)i * Mp + j] * m.Td[(size_t)i * Mp + j];
-        xo[x] = v < 1e-20 ? 1e-20 : v;
+        xo[x] = nan_tail ? nan("") : (v < 1e-20 ? 1e-20 : v);    // (NaN < 1e-20 is false: the reference's floor keeps a NaN)
+    }
+    if (nan_tail) {
+        __syncthreads();
+        for (int x = tid; x < K * M; x += nth)
+            if (w.poison[(size_t)t * K + x / M]) gso[x] = nan("");
     }
     // gamma0 = alpha_hat_0 o beta_0; src/hmm.cpp:150
     const int c0 = p.chunk_off[t];
     const float *a0 = w.alpha + p.col_off[t] * Mp;
-    for (int j = tid; j < M; j += nth) w.gamma0[(size_t)t * M + j] = (double)a0[j] * w.beta_out[(size_t)c0 * Mp + j];
+    for (int j = tid; j < M; j += nth) w.gamma0[(size_t)t * M + j] = nan_tail ? nan("") : (double)a0[j] * w.beta_out[(size_t)c0 * Mp + j];
     // ll = sum of the chunk log-normalisers (warp 0, fixed order)
     if (tid < 32) {
         double acc = 0.0;
@@ -888,6 +894,7 @@ __global__ void __launch_bounds__(256) k_stats_literal(Model m, Plan p, Work w)
             }
             __syncthreads();
             const double C = red_s[0];
+            if (tid == 0 && !(C == C)) atomicMax(&w.nanpos[t], bi);
             if (tid < M) gsl[tid] += dg_s[tid] * C;
             for (size_t x = tid; x < MM; x += nth) {
                 const int i = (int)(x / Mp), j = (int)(x % Mp);
@@ -902,9 +909,23 @@ __global__ void __launch_bounds__(256) k_stats_literal(Model m, Plan p, Work w)
     }
 }
 
+// keys of the blocks at or before the last NaN constant of their contig (see Work::nanpos)
+__global__ void k_poison_keys(Model m, Plan p, Work w)
+{
+    const int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (x >= p.total_blocks) return;
+    int t = 0;
+    while (t + 1 < p.n_contigs && p.blk_off[t + 1] <= x) ++t;
+    const int b = (int)(x - p.blk_off[t]);
+    if (b <= w.nanpos[t]) w.poison[(size_t)t * m.K + (p.kcode[x] & kKeyMask)] = 1;
+}
+
 void launch_stats_literal(const Model &m, const Plan &p, const Work &w, cudaStream_t st)
 {
+    cudaMemsetAsync(w.nanpos, 0xff, (size_t)p.n_contigs * sizeof(int), st);
+    cudaMemsetAsync(w.poison, 0, (size_t)p.n_contigs * m.K, st);
     k_stats_literal<<<p.n_slabs, 256, 0, st>>>(m, p, w);
+    k_poison_keys<<<(unsigned)((p.total_blocks + 255) / 256), 256, 0, st>>>(m, p, w);
 }
 
 // d~^span for every (eigen key, distinct span): Model::pwtab

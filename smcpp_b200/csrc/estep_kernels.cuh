@@ -138,6 +138,9 @@ struct Work {
     double *Xlit;            // [n_slabs][Mp*Mp]       literal-path partials of X (irregular eigen keys only; else nullptr)
     double *gslit;           // [n_slabs][n_eig][Mp]   literal-path partials of the gamma sums of the eigen keys
     double *lit_scratch;     // [n_slabs][2][Mp*Mp]
+    int *nanpos;             // [C] literal path: last block (highest index) whose normalising constant is NaN, -1 = none.  The
+                             // reference carries that constant into beta (log_C, src/hmm.cpp:117-127): every block before it is NaN too
+    uint8_t *poison;         // [C][K] keys that occur at or before nanpos: their gamma sums are NaN in the reference
     // outputs (device)
     double *ll;              // [C]
     double *xisum;           // [C][M][M]
