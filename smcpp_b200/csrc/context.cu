@@ -104,11 +104,6 @@ struct smcpp_b200_ctx {
     DevBuf<int64_t> d_it_start;
     int n_items = 0;
     DevBuf<int> d_eig_of_key, d_key_of_eig;
-    DevBuf<int64_t> d_sf_off, d_sb_off;     // precompiled recursion schedule (Plan::sf_* / sb_*)
-    DevBuf<uint32_t> d_sf_hdr, d_sb_hdr;
-    DevBuf<int4> d_sf_rec;
-    DevBuf<int2> d_sb_rec;
-    int sched_G = 0, sched_burn = -1, sched_burn_f = -1;   // burn-in lengths the schedule was built for
 
     // ---- options
     int opt_chunk_blocks = 0;       // 0 = auto
@@ -209,9 +204,6 @@ struct smcpp_b200_ctx {
         p.srec = d_srec.p; p.seg = d_seg.p;
         p.n_items = n_items; p.erec = d_erec.p; p.it_start = d_it_start.p; p.it_len = d_it_len.p; p.it_contig = d_it_contig.p;
         p.it_eig = d_it_eig.p; p.it_off = d_it_off.p;
-        p.sched_G = sched_G;
-        p.sf_off = d_sf_off.p; p.sf_hdr = d_sf_hdr.p; p.sf_rec = d_sf_rec.p;
-        p.sb_off = d_sb_off.p; p.sb_hdr = d_sb_hdr.p; p.sb_rec = d_sb_rec.p;
         return p;
     }
     Work work() const
@@ -309,7 +301,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->d_chunk_off.release(); ctx->d_slab_off.release(); ctx->d_ch_contig.release(); ctx->d_ch_start.release();
     ctx->d_ch_len.release(); ctx->d_sl_contig.release(); ctx->d_sl_start.release(); ctx->d_sl_len.release();
     ctx->d_sl_mask.release(); ctx->d_ct_mask.release(); ctx->m_irregular.release(); ctx->w_nanpos.release(); ctx->w_poison.release(); ctx->w_Xlit.release(); ctx->w_gslit.release(); ctx->w_lit_scratch.release(); ctx->q_in.release(); ctx->q_terms.release(); ctx->q_out.release(); ctx->d_present.release(); ctx->d_key_nb.release(); ctx->d_srec.release(); ctx->d_seg.release(); ctx->d_erec.release(); ctx->d_it_len.release(); ctx->d_it_contig.release();
-    ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release(); ctx->d_sf_off.release(); ctx->d_sb_off.release(); ctx->d_sf_hdr.release(); ctx->d_sb_hdr.release(); ctx->d_sf_rec.release(); ctx->d_sb_rec.release();
+    ctx->d_it_eig.release(); ctx->d_it_off.release(); ctx->d_it_start.release(); ctx->w_uvec.release(); ctx->w_Ritem.release(); ctx->w_ditem.release(); ctx->d_eig_of_key.release(); ctx->d_key_of_eig.release();
     ctx->d_in.release(); ctx->h_in.release();
     ctx->m_pi.release(); ctx->m_Td.release(); ctx->m_TdT.release(); ctx->m_E.release(); ctx->m_P.release();
     ctx->m_PT.release(); ctx->m_Pinv.release(); ctx->m_PinvT.release(); ctx->m_dsc.release(); ctx->m_logd.release();
@@ -355,7 +347,6 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "fwd_cached_keys") ctx->rec.cached_keys = std::max(0, std::min(4, (int)value));
     else if (n == "fused_recursions") ctx->rec.fused = value != 0;
     else if (n == "tiles") ctx->rec.tiles = value >= 2 ? 2 : 1;
-    else if (n == "schedule") ctx->rec.schedule = value != 0;
     else if (n == "stats_streams") ctx->opt_stats_streams = value >= 2 ? 2 : 1;
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
@@ -543,125 +534,6 @@ int64_t smcpp_b200_total_blocks(const smcpp_b200_ctx *ctx) { return ctx ? ctx->t
 
 }  // extern "C"
 
-// ---- precompiled lockstep schedule of the tensor-path recursions (Plan::sf_* / sb_*) -------------------------------------
-// A warp of k_forward_mma / k_backward_mma advances its G chunks in rounds of ONE block type: the least advanced chunk
-// (ties: the lowest slot) picks the type of its current block, every chunk whose current block has that type commits.
-// The policy reads nothing but the observations, so it is played once here, per plan, and the kernels read the outcome.
-static int build_schedule(smcpp_b200_ctx *ctx, int G, const std::vector<int32_t> &ch_contig, const std::vector<int32_t> &ch_start,
-                          const std::vector<int32_t> &ch_len, int burn_fwd, int burn_bwd)
-{
-    const int n_chunks = (int)ch_contig.size();
-    const int W = (n_chunks + G - 1) / G;
-    std::vector<int64_t> off_f(W + 1, 0), off_b(W + 1, 0);
-    std::vector<uint32_t> hdr_f, hdr_b;
-    std::vector<int4> rec_f;
-    std::vector<int2> rec_b;
-    // (sizes are known up to the rare out-of-step rounds: reserve the in-step size)
-    {
-        int64_t rf = 0, rb = 0;
-        for (int wg = 0; wg < W; ++wg) {
-            int mf = 0, mb = 0;
-            for (int n = 0; n < G && wg * G + n < n_chunks; ++n) {
-                const int c = wg * G + n;
-                mf = std::max(mf, ch_len[c] + std::min(burn_fwd, ch_start[c]));
-                mb = std::max(mb, ch_len[c] + burn_bwd);
-            }
-            rf += mf; rb += mb;
-        }
-        hdr_f.reserve(rf + rf / 64); rec_f.reserve((rf + rf / 64) * 8);
-        hdr_b.reserve(rb + rb / 64); rec_b.reserve((rb + rb / 64) * 8);
-    }
-    const kcode_t *kcode = ctx->h_key.data();
-    const int32_t *span = ctx->h_span.data(), *span_id = ctx->h_span_id.data();
-    for (int wg = 0; wg < W; ++wg) {
-        int64_t g0[8];
-        int cur[8], end[8], done[8];
-        bool act[8];
-        // ---- forward: ascending from the burn-in start to the chunk's end
-        for (int n = 0; n < 8; ++n) {
-            const int c = wg * G + n;
-            act[n] = n < G && c < n_chunks;
-            done[n] = 0;
-            if (!act[n]) { g0[n] = 0; cur[n] = end[n] = 0; continue; }
-            g0[n] = ctx->blk_off[ch_contig[c]];
-            cur[n] = std::max(0, ch_start[c] - burn_fwd);
-            end[n] = ch_start[c] + ch_len[c];
-            act[n] = cur[n] < end[n];
-        }
-        for (;;) {
-            int lead = -1;
-            for (int n = 0; n < 8; ++n)
-                if (act[n] && (lead < 0 || done[n] < done[lead])) lead = n;
-            if (lead < 0) break;
-            const uint32_t T = kcode[g0[lead] + cur[lead]] >> kKeyBits;
-            uint32_t mask = 0;
-            for (int n = 0; n < 8; ++n) {
-                int4 r = make_int4(0, 0, 1, 0);
-                if (act[n]) {
-                    const int64_t x = g0[n] + cur[n];
-                    r = make_int4((int)kcode[x], span_id[x], span[x], 0);
-                    if ((kcode[x] >> kKeyBits) == T) mask |= 1u << n;
-                }
-                rec_f.push_back(r);
-            }
-            hdr_f.push_back(T | (mask << 16));
-            for (int n = 0; n < 8; ++n)
-                if (mask & (1u << n)) { ++cur[n]; ++done[n]; act[n] = cur[n] < end[n]; }
-        }
-        off_f[wg + 1] = (int64_t)hdr_f.size();
-        // ---- backward: descending from the burn-in start (right of the chunk) to the chunk's first block
-        int lo[8];
-        for (int n = 0; n < 8; ++n) {
-            const int c = wg * G + n;
-            act[n] = n < G && c < n_chunks;
-            done[n] = 0;
-            lo[n] = 0;
-            if (!act[n]) { g0[n] = 0; cur[n] = -1; continue; }
-            const int t = ch_contig[c];
-            g0[n] = ctx->blk_off[t];
-            const int L = (int)(ctx->blk_off[t + 1] - ctx->blk_off[t]);
-            const int bend = ch_start[c] + ch_len[c];
-            int b1 = bend + burn_bwd;
-            if (b1 > L || bend == L) b1 = L;
-            cur[n] = b1 - 1;
-            lo[n] = ch_start[c];
-            act[n] = cur[n] >= lo[n];
-        }
-        for (;;) {
-            int lead = -1;
-            for (int n = 0; n < 8; ++n)
-                if (act[n] && (lead < 0 || done[n] < done[lead])) lead = n;
-            if (lead < 0) break;
-            const uint32_t T = kcode[g0[lead] + cur[lead]] >> kKeyBits;
-            uint32_t mask = 0;
-            for (int n = 0; n < 8; ++n) {
-                int2 r = make_int2(0, 0);
-                if (act[n]) {
-                    const int64_t x = g0[n] + cur[n];
-                    r = make_int2((int)kcode[x], span_id[x]);
-                    if ((kcode[x] >> kKeyBits) == T) mask |= 1u << n;
-                }
-                rec_b.push_back(r);
-            }
-            hdr_b.push_back(T | (mask << 16));
-            for (int n = 0; n < 8; ++n)
-                if (mask & (1u << n)) { --cur[n]; ++done[n]; act[n] = cur[n] >= lo[n]; }
-        }
-        off_b[wg + 1] = (int64_t)hdr_b.size();
-    }
-    // one padding round at the end: the kernels prefetch two rounds ahead with a clamped index
-    hdr_f.push_back(0); hdr_b.push_back(0);
-    for (int n = 0; n < 8; ++n) { rec_f.push_back(make_int4(0, 0, 1, 0)); rec_b.push_back(make_int2(0, 0)); }
-#define UPS(buf, vec)                                                                                            \
-    CU(ctx->buf.ensure((vec).size()));                                                                           \
-    CU(cudaMemcpy(ctx->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
-    UPS(d_sf_off, off_f); UPS(d_sf_hdr, hdr_f); UPS(d_sf_rec, rec_f);
-    UPS(d_sb_off, off_b); UPS(d_sb_hdr, hdr_b); UPS(d_sb_rec, rec_b);
-#undef UPS
-    ctx->sched_G = G;
-    return 0;
-}
-
 // ---- chunk / slab plan and buffer allocation --------------------------------------------------------
 static int make_plan(smcpp_b200_ctx *ctx, int M)
 {
@@ -734,9 +606,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
         const int64_t per = ctx->total / ((int64_t)ctx->n_sm * 8);
         slab = (int)std::min<int64_t>(16384, std::max<int64_t>(2048, (per / 32) * 32));
     }
-    const int burn_f_now = std::max(0, std::min(burn, ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt));
-    const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M && ctx->plan_literal == ctx->literal_mode &&
-                      (ctx->sched_G == 0 || (ctx->sched_burn == burn && ctx->sched_burn_f == burn_f_now));
+    const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M && ctx->plan_literal == ctx->literal_mode;
     ctx->plan_burn = burn;
     if (same) return 0;
     ctx->plan_valid = false;   // a failure below must not leave the previous plan looking current
@@ -844,15 +714,6 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
             }
         }
         it_off.push_back((int32_t)it_len.size());
-    }
-    ctx->sched_G = 0;
-    if ((Mp == 32 || Mp == 64 || Mp == 128) && (int)ch_contig.size() >= ctx->opt_mma_min_chunks && !ctx->opt_force_sequential &&
-        !ctx->literal_mode && ctx->rec.schedule) {
-        const int G = mma_chunks_per_warp((int)ch_contig.size(), ctx->n_sm, ctx->rec);
-        const int burn_f = std::max(0, std::min(burn, ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt));
-        if (build_schedule(ctx, G, ch_contig, ch_start, ch_len, burn_f, burn)) return 1;
-        ctx->sched_burn = burn;
-        ctx->sched_burn_f = burn_f;
     }
     ctx->n_items = (int)it_len.size();
     ctx->n_chunks = (int)ch_contig.size();

@@ -106,18 +106,6 @@ struct Plan {
     const int32_t *it_contig;// [n_items]
     const int32_t *it_eig;   // [n_items]
     const int32_t *it_off;   // [C * n_eig + 1] first item of (contig, eigen key)
-    // Precompiled lockstep schedule of the tensor-path recursions (recursion_mma.cu; built per plan, context.cu:
-    // build_schedule).  Which block type a round has and which of a warp's chunks commit depends on the observations only,
-    // so it is decided once per data set instead of with ballots / reductions / shuffles in every round of every E-step;
-    // the per-block codes arrive as one coalesced record per round.
-    int sched_G;             // chunks per warp the schedule was built for (0: no schedule)
-    const int64_t *sf_off;   // [n_warps + 1] forward: first round of each warp
-    const uint32_t *sf_hdr;  // [rounds]      bits 0-15 block type T of the round (0: span 1, 1 + e: span > 1 with eigen key e),
-                             //               bits 16-23 chunk slots that commit
-    const int4 *sf_rec;      // [rounds][8]   (kcode, span id, span, 0) of each slot's current block
-    const int64_t *sb_off;   // backward: the same, records (kcode, span id)
-    const uint32_t *sb_hdr;
-    const int2 *sb_rec;
 };
 
 __host__ __device__ inline bool mask_bit(const uint32_t *mask, int bit) { return (mask[bit >> 5] >> (bit & 31)) & 1u; }
@@ -178,7 +166,6 @@ struct RecOpts {             // per-context tuning of the tensor-path recursions
     int cached_keys = 0;     // span-1 keys whose float step matrix is resident in shared memory (M <= 32), 0..4 (measured: no gain, the
                              // LSU data pipe carries the same bytes into the registers either way)
     int force_G = 0;         // chunks per warp pinned to 1 / 2 / 4 / 8 (0 = automatic)
-    int schedule = 1;        // precompiled lockstep schedule (Plan::sf_* / sb_*) instead of deciding every round in the kernel
     int fused = 0;           // forward and backward recursion in one launch (measured slower than two streams: 8.2 vs 7.65 ms on C3)
     int tiles = 1;           // MMA row tiles per warp at M <= 32: 1 = recursion_mma.cu (8 chunks per warp); 2 = recursion_mma2.cu (16 chunks per
                              // warp: half the LSU traffic per chunk step, but 255 registers leave one warp per scheduler -- measured slower, 9.9 vs 7.6 ms)
@@ -191,7 +178,6 @@ void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, 
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);
 int resident_warps_mma(int n_sm, int Mp, const RecOpts &o);
 bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o);
-int mma_chunks_per_warp(int n_chunks, int n_sm, const RecOpts &o);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);

@@ -262,7 +262,7 @@ struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of t
 // FRAG: where the B fragments of the hot eigen key live -- registers (NS = 1 only: 2 x 64 registers, at most 8 warps/SM,
 // forward and backward then run one after the other), shared memory (all warps of both kernels resident at once) or
 // global memory through the read-only path (M = 128: a fragment table is 128 KB).  The launcher picks.
-template <int NS, int FRAG, bool SCHED>
+template <int NS, int FRAG>
 __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int nkc, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP, XS = MP + 4;
@@ -336,24 +336,8 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
         o.sp_hi = p.span[i1]; o.kc_hi = p.kcode[i1]; o.id_hi = p.span_id[i1];
         return o;
     };
-    // SCHED: the precompiled schedule of this warp (Plan::sf_*): per round a header (block type, who commits) and one
-    // record per chunk slot; fetched two rounds ahead
-    const int wg = bid * kMW + warp;
-    int64_t r0 = 0;
-    int R = 0;
-    const int4 *rp = nullptr;
-    int4 rc = make_int4(0, 0, 1, 0), rc1 = rc, rc2 = rc;
-    uint32_t hd = 0, hd1 = 0, hd2 = 0;
-    if constexpr (SCHED) {
-        r0 = p.sf_off[wg];
-        R = (int)(p.sf_off[wg + 1] - r0);
-        rp = p.sf_rec + r0 * 8 + n;
-        rc = __ldg(rp); rc1 = __ldg(rp + 8);                 // (one padding round follows the last warp's schedule)
-        hd = __ldg(p.sf_hdr + r0); hd1 = __ldg(p.sf_hdr + r0 + 1);
-    } else {
-        ob = load_batch(base);
-        obn = load_batch(base + 8);
-    }
+    ob = load_batch(base);
+    obn = load_batch(base + 8);
     double llsum = 0.0, lprod = 1.0;
     int lcnt = 0, done = 0, rounds = 0;
     // (span, code, span id) of the chunk's current block and, for a span>1 block, its d~^span vector: fetched at the END
@@ -361,15 +345,11 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
     // (ptxas sinks a load issued inside the round down to its first use).
     int span, kc, sid;
     auto fetch_cur = [&]() {
-        if constexpr (SCHED) {
-            kc = rc.x; sid = rc.y; span = rc.z;
-        } else {
-            const int pos = cur - base;
-            const int src = (lane & ~3) | (pos & 3);
-            span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
-            kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
-            sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
-        }
+        const int pos = cur - base;
+        const int src = (lane & ~3) | (pos & 3);
+        span = __shfl_sync(kAll, (pos & 4) ? ob.sp_hi : ob.sp_lo, src);
+        kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
     };
     double2 pwv[NT];
 #pragma unroll
@@ -382,27 +362,15 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
     fetch_cur();
     if (active && (kc >> kKeyBits) > 0) load_pw();
 
-    for (int r = 0;; ++r) {
-        int T;
-        bool adv;
-        if constexpr (SCHED) {
-            if (r >= R) break;
-            ++rounds;
-            T = (int)(hd & 0xffffu);
-            adv = (hd >> (16 + n)) & 1u;
-            // two rounds ahead (the index stays inside the schedule: one padding round at its very end)
-            rc2 = __ldg(rp + (size_t)min(r + 2, R) * 8);
-            hd2 = __ldg(p.sf_hdr + r0 + min(r + 2, R));
-        } else {
-            const unsigned am = __ballot_sync(kAll, active);
-            if (!am) break;
-            ++rounds;
-            const int type = active ? (kc >> kKeyBits) : -1;
-            // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
-            const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
-            T = __shfl_sync(kAll, type, lead & 31);
-            adv = active && type == T;
-        }
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        ++rounds;
+        const int type = active ? (kc >> kKeyBits) : -1;
+        // the least advanced chunk picks the round's block type (no chunk can starve, phases re-align by themselves)
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
         const int k = adv ? (kc & kKeyMask) : (nkc > 0 ? m.hot_keys[0] : 0);
         float xn[NI];
         double cmul = 1.0, cadd = 0.0;
@@ -509,27 +477,21 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
             ++done;
             if (cur >= bend) active = false;
         }
-        int kc2;   // code of the block after the next one of this chunk (L1 prefetch of its step matrix below)
-        if constexpr (SCHED) {
-            rc = rc1; rc1 = rc2; hd = hd1; hd1 = hd2;
-            fetch_cur();
-            if (adv && (kc >> kKeyBits) > 0) load_pw();
-            kc2 = rc1.x;
-        } else {
+        {
             const bool rot = adv && active && cur - base == 8;
             if (rot) { base += 8; ob = obn; }
             const int64_t i0 = g0 + min(base + 8 + q, bend - 1), i1 = g0 + min(base + 12 + q, bend - 1);
             ldg_if(obn.sp_lo, p.span + i0, rot); ldg_if(obn.kc_lo, p.kcode + i0, rot); ldg_if(obn.id_lo, p.span_id + i0, rot);
             ldg_if(obn.sp_hi, p.span + i1, rot); ldg_if(obn.kc_hi, p.kcode + i1, rot); ldg_if(obn.id_hi, p.span_id + i1, rot);
-            fetch_cur();
-            if (adv && active && (kc >> kKeyBits) > 0) load_pw();
-            const int pos2 = cur + 1 - base;
-            const int v2 = pos2 < 8 ? ((pos2 & 4) ? ob.kc_hi : ob.kc_lo) : obn.kc_lo;
-            kc2 = __shfl_sync(kAll, v2, (lane & ~3) | (pos2 & 3));
         }
+        fetch_cur();
+        if (adv && active && (kc >> kKeyBits) > 0) load_pw();
         if constexpr (NS == 1) {
             // float step matrix of the block AFTER the next one -> L1 (one full round ahead).  The matrices of the rare keys
             // (60+ full-SFS keys, 4 KB each) do not stay in L1; without this every 4-row group of their GEMV waits on L2.
+            const int pos2 = cur + 1 - base;
+            const int v2 = pos2 < 8 ? ((pos2 & 4) ? ob.kc_hi : ob.kc_lo) : obn.kc_lo;
+            const int kc2 = __shfl_sync(kAll, v2, (lane & ~3) | (pos2 & 3));
             bool resident = (kc2 & kKeyMask) == m.hot_keys[0];
             for (int sl = 1; sl < nkc; ++sl) resident = resident || (kc2 & kKeyMask) == m.hot_keys[sl];
             if (adv && active && cur + 1 < bend && (kc2 >> kKeyBits) == 0 && !resident) {
@@ -548,7 +510,7 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
 }
 
 // =============================================== backward ==================================================
-template <int NS, int FRAG, bool SCHED>
+template <int NS, int FRAG>
 __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP;
@@ -610,36 +572,17 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
         o.kc_hi = p.kcode[i1]; o.id_hi = p.span_id[i1];
         return o;
     };
-    // SCHED: the precompiled schedule of this warp (Plan::sb_*), see the forward kernel
-    const int wg = bid * kMW + (tid >> 5);
-    int64_t r0 = 0;
-    int R = 0;
-    const int2 *rp = nullptr;
-    int2 rc = make_int2(0, 0), rc1 = rc, rc2 = rc;
-    uint32_t hd = 0, hd1 = 0, hd2 = 0;
-    if constexpr (SCHED) {
-        r0 = p.sb_off[wg];
-        R = (int)(p.sb_off[wg + 1] - r0);
-        rp = p.sb_rec + r0 * 8 + n;
-        rc = __ldg(rp); rc1 = __ldg(rp + 8);
-        hd = __ldg(p.sb_hdr + r0); hd1 = __ldg(p.sb_hdr + r0 + 1);
-    } else {
-        ob = load_batch(top);
-        obn = load_batch(top - 8);
-    }
+    ob = load_batch(top);
+    obn = load_batch(top - 8);
     int since = 0, done = 0;
     // code and span id of the chunk's current block and the vector that multiplies inside its step -- d~^span (span > 1)
     // or e_k (span 1), both q-major -- fetched at the END of the previous round (see the forward kernel)
     int kc, sid;
     auto fetch_cur = [&]() {
-        if constexpr (SCHED) {
-            kc = rc.x; sid = rc.y;
-        } else {
-            const int pos = top - cur;
-            const int src = (lane & ~3) | (pos & 3);
-            kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
-            sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
-        }
+        const int pos = top - cur;
+        const int src = (lane & ~3) | (pos & 3);
+        kc = __shfl_sync(kAll, (pos & 4) ? ob.kc_hi : ob.kc_lo, src);
+        sid = __shfl_sync(kAll, (pos & 4) ? ob.id_hi : ob.id_lo, src);
     };
     double2 opv[NT];
 #pragma unroll
@@ -654,23 +597,13 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
     fetch_cur();
     if (active) load_op();
 
-    for (int r = 0;; ++r) {
-        int T;
-        bool adv;
-        if constexpr (SCHED) {
-            if (r >= R) break;
-            T = (int)(hd & 0xffffu);
-            adv = (hd >> (16 + n)) & 1u;
-            rc2 = __ldg(rp + (size_t)min(r + 2, R) * 8);
-            hd2 = __ldg(p.sb_hdr + r0 + min(r + 2, R));
-        } else {
-            const unsigned am = __ballot_sync(kAll, active);
-            if (!am) break;
-            const int type = active ? (kc >> kKeyBits) : -1;
-            const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
-            T = __shfl_sync(kAll, type, lead & 31);
-            adv = active && type == T;
-        }
+    for (;;) {
+        const unsigned am = __ballot_sync(kAll, active);
+        if (!am) break;
+        const int type = active ? (kc >> kKeyBits) : -1;
+        const unsigned lead = __reduce_min_sync(kAll, active ? (((unsigned)done << 5) | (unsigned)lane) : 0xffffffffu);
+        const int T = __shfl_sync(kAll, type, lead & 31);
+        const bool adv = active && type == T;
         // the chunk's verified start value: normalised, recorded before the first stored step
         const bool rec = adv && cur == bend - 1;
         if (__any_sync(kAll, rec)) {
@@ -741,19 +674,15 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
         } else {
             --since;
         }
-        if constexpr (SCHED) {
-            rc = rc1; rc1 = rc2; hd = hd1; hd1 = hd2;
-            fetch_cur();
-            if (adv && active) load_op();
-        } else {
+        {
             const bool rot = adv && active && top - cur == 8;
             if (rot) { top -= 8; ob = obn; }
             const int64_t i0 = g0 + max(top - 8 - q, s), i1 = g0 + max(top - 12 - q, s);
             ldg_if(obn.kc_lo, p.kcode + i0, rot); ldg_if(obn.id_lo, p.span_id + i0, rot);
             ldg_if(obn.kc_hi, p.kcode + i1, rot); ldg_if(obn.id_hi, p.span_id + i1, rot);
-            fetch_cur();
-            if (adv && active) load_op();
         }
+        fetch_cur();
+        if (adv && active) load_op();
     }
     if (c < p.n_chunks) {
         double part = 0.0;
@@ -766,16 +695,16 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
     }
 }
 
-template <int NS, int FRAG, bool SCHED>
+template <int NS, int FRAG>
 __global__ void __launch_bounds__(kMW * 32) k_forward_mma(Model m, Plan p, Work w, int G, int nkc)
 {
-    forward_mma_body<NS, FRAG, SCHED>(m, p, w, G, nkc, blockIdx.x);
+    forward_mma_body<NS, FRAG>(m, p, w, G, nkc, blockIdx.x);
 }
 
-template <int NS, int FRAG, bool SCHED>
+template <int NS, int FRAG>
 __global__ void __launch_bounds__(kMW * 32) k_backward_mma(Model m, Plan p, Work w, int G)
 {
-    backward_mma_body<NS, FRAG, SCHED>(m, p, w, G, blockIdx.x);
+    backward_mma_body<NS, FRAG>(m, p, w, G, blockIdx.x);
 }
 
 // Both recursions in ONE launch: the forward and the backward pass are independent (the statistics need both), and they
@@ -790,8 +719,8 @@ template <int NS, int FRAG>
 __global__ void __launch_bounds__(kMW * 32) k_recursions_mma(Model m, Plan p, Work w, int G, int nkc, int blocks)
 {
     const int bid = blockIdx.x;
-    if (bid < blocks) backward_mma_body<NS, FRAG, false>(m, p, w, G, bid);
-    else forward_mma_body<NS, FRAG, false>(m, p, w, G, nkc, bid - blocks);
+    if (bid < blocks) backward_mma_body<NS, FRAG>(m, p, w, G, bid);
+    else forward_mma_body<NS, FRAG>(m, p, w, G, nkc, bid - blocks);
 }
 
 // ---- launch -------------------------------------------------------------------------------------------------
@@ -822,14 +751,14 @@ int resident_warps_mma(int n_sm, int Mp, const RecOpts &o)
     int bf = 0, bb = 0;
     if (Mp == 32) {
         const int nkc = o.cached_keys < 0 ? 0 : (o.cached_keys > 4 ? 4 : o.cached_keys);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<1, kFragShared, true>, kMW * 32, fwd_smem(1, kFragShared, nkc));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<1, kFragShared, true>, kMW * 32, bwd_smem(1, kFragShared));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<1, kFragShared>, kMW * 32, fwd_smem(1, kFragShared, nkc));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<1, kFragShared>, kMW * 32, bwd_smem(1, kFragShared));
     } else if (Mp == 64) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<2, kFragShared, true>, kMW * 32, fwd_smem(2, kFragShared, 0));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<2, kFragShared, true>, kMW * 32, bwd_smem(2, kFragShared));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<2, kFragShared>, kMW * 32, fwd_smem(2, kFragShared, 0));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<2, kFragShared>, kMW * 32, bwd_smem(2, kFragShared));
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<4, kFragGlobal, true>, kMW * 32, fwd_smem(4, kFragGlobal, 0));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<4, kFragGlobal, true>, kMW * 32, bwd_smem(4, kFragGlobal));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, k_forward_mma<4, kFragGlobal>, kMW * 32, fwd_smem(4, kFragGlobal, 0));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_mma<4, kFragGlobal>, kMW * 32, bwd_smem(4, kFragGlobal));
     }
     int b = bf < bb ? bf : bb;
     if (b < 1) b = 1;
@@ -846,8 +775,6 @@ static int chunks_per_warp(int n_chunks, int n_sm, const RecOpts &o)
     while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
     return G;
 }
-
-int mma_chunks_per_warp(int n_chunks, int n_sm, const RecOpts &o) { return chunks_per_warp(n_chunks, n_sm, o); }
 
 // The tensor-path forward kernel gives each chunk only 4 lanes for the float GEMV of the span-1 step; above 32 states
 // that only pays off when every warp has its full 8 chunks, otherwise the one-chunk-per-warp kernel is used
@@ -870,35 +797,20 @@ static void configure_once()
 {
     static std::atomic<size_t> done[kMaxDevices];
     if (!needs_smem_config(done, 1)) return;
-    set_attrs(k_forward_mma<1, kFragReg, true>, fwd_smem(1, kFragReg, 4));
-    set_attrs(k_forward_mma<1, kFragShared, true>, fwd_smem(1, kFragShared, 4));
-    set_attrs(k_backward_mma<1, kFragReg, true>, bwd_smem(1, kFragReg));
-    set_attrs(k_backward_mma<1, kFragShared, true>, bwd_smem(1, kFragShared));
-    set_attrs(k_forward_mma<2, kFragShared, true>, fwd_smem(2, kFragShared, 0));
-    set_attrs(k_backward_mma<2, kFragShared, true>, bwd_smem(2, kFragShared));
-    set_attrs(k_forward_mma<4, kFragGlobal, true>, fwd_smem(4, kFragGlobal, 0));
-    set_attrs(k_backward_mma<4, kFragGlobal, true>, bwd_smem(4, kFragGlobal));
-    set_attrs(k_forward_mma<1, kFragReg, false>, fwd_smem(1, kFragReg, 4));
-    set_attrs(k_forward_mma<1, kFragShared, false>, fwd_smem(1, kFragShared, 4));
-    set_attrs(k_backward_mma<1, kFragReg, false>, bwd_smem(1, kFragReg));
-    set_attrs(k_backward_mma<1, kFragShared, false>, bwd_smem(1, kFragShared));
-    set_attrs(k_forward_mma<2, kFragShared, false>, fwd_smem(2, kFragShared, 0));
-    set_attrs(k_backward_mma<2, kFragShared, false>, bwd_smem(2, kFragShared));
-    set_attrs(k_forward_mma<4, kFragGlobal, false>, fwd_smem(4, kFragGlobal, 0));
-    set_attrs(k_backward_mma<4, kFragGlobal, false>, bwd_smem(4, kFragGlobal));
+    set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg, 4));
+    set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared, 4));
+    set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));
+    set_attrs(k_backward_mma<1, kFragShared>, bwd_smem(1, kFragShared));
+    set_attrs(k_forward_mma<2, kFragShared>, fwd_smem(2, kFragShared, 0));
+    set_attrs(k_backward_mma<2, kFragShared>, bwd_smem(2, kFragShared));
+    set_attrs(k_forward_mma<4, kFragGlobal>, fwd_smem(4, kFragGlobal, 0));
+    set_attrs(k_backward_mma<4, kFragGlobal>, bwd_smem(4, kFragGlobal));
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
     set_attrs(k_recursions_mma<1, kFragReg>, mx(fwd_smem(1, kFragReg, 4), bwd_smem(1, kFragReg)));
     set_attrs(k_recursions_mma<1, kFragShared>, mx(fwd_smem(1, kFragShared, 4), bwd_smem(1, kFragShared)));
     set_attrs(k_recursions_mma<2, kFragShared>, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)));
     set_attrs(k_recursions_mma<4, kFragGlobal>, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)));
 }
-
-// the schedule-driven kernel when the plan carries a schedule built for this chunks-per-warp count, else the self-scheduling one
-#define LAUNCH_SCHED(kernel, NS_, FRAG_, smem, args)                                              \
-    do {                                                                                          \
-        if (p.sched_G == G) kernel<NS_, FRAG_, true><<<blocks, kMW * 32, smem, st>>> args;         \
-        else kernel<NS_, FRAG_, false><<<blocks, kMW * 32, smem, st>>> args;                       \
-    } while (0)
 
 void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
@@ -907,12 +819,12 @@ void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, 
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
     if (m.Mp == 32) {
         const int nkc = cached_keys(m, o);
-        if (use_reg_frags(warps, n_sm)) LAUNCH_SCHED(k_forward_mma, 1, kFragReg, fwd_smem(1, kFragReg, nkc), (m, p, w, G, nkc));
-        else LAUNCH_SCHED(k_forward_mma, 1, kFragShared, fwd_smem(1, kFragShared, nkc), (m, p, w, G, nkc));
+        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, G, nkc);
+        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared, nkc), st>>>(m, p, w, G, nkc);
     } else if (m.Mp == 64) {
-        LAUNCH_SCHED(k_forward_mma, 2, kFragShared, fwd_smem(2, kFragShared, 0), (m, p, w, G, 0));
+        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared, 0), st>>>(m, p, w, G, 0);
     } else {
-        LAUNCH_SCHED(k_forward_mma, 4, kFragGlobal, fwd_smem(4, kFragGlobal, 0), (m, p, w, G, 0));
+        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal, 0), st>>>(m, p, w, G, 0);
     }
 }
 
@@ -922,12 +834,12 @@ void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm,
     const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
     if (m.Mp == 32) {
-        if (use_reg_frags(warps, n_sm)) LAUNCH_SCHED(k_backward_mma, 1, kFragReg, bwd_smem(1, kFragReg), (m, p, w, G));
-        else LAUNCH_SCHED(k_backward_mma, 1, kFragShared, bwd_smem(1, kFragShared), (m, p, w, G));
+        if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, G);
+        else k_backward_mma<1, kFragShared><<<blocks, kMW * 32, bwd_smem(1, kFragShared), st>>>(m, p, w, G);
     } else if (m.Mp == 64) {
-        LAUNCH_SCHED(k_backward_mma, 2, kFragShared, bwd_smem(2, kFragShared), (m, p, w, G));
+        k_backward_mma<2, kFragShared><<<blocks, kMW * 32, bwd_smem(2, kFragShared), st>>>(m, p, w, G);
     } else {
-        LAUNCH_SCHED(k_backward_mma, 4, kFragGlobal, bwd_smem(4, kFragGlobal), (m, p, w, G));
+        k_backward_mma<4, kFragGlobal><<<blocks, kMW * 32, bwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
     }
 }
 

@@ -73,26 +73,6 @@ def test_golden_chunked_tensor_path(name, chunk, burn, tiles):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("G,chunk,burn", [(8, 48, 512), (2, 100, 64), (4, 16, 0), (0, 37, 300)])
-def test_precompiled_schedule_is_bitwise_the_in_kernel_schedule(name, G, chunk, burn):
-    """The lockstep policy of the tensor-path recursions played once per plan on the host (Plan::sf_* / sb_*) against the
-    same policy decided round by round inside the kernels: identical results, including ragged contigs, contigs of one
-    block, chunk counts that do not fill a warp and burn-ins that are clipped at a contig's start."""
-    g = Golden(name)
-    opts = {"chunk_blocks": chunk, "burn_in_blocks": burn, "mma_min_chunks": 1, "force_mma_forward": 1, "chunks_per_warp": G}
-    ctx1, a = run_ctx(g.contigs, g.npop, g.ref, dict(opts, schedule=0))
-    ctx2, b = run_ctx(g.contigs, g.npop, g.ref, dict(opts, schedule=1))
-    for k in ("ll", "xisum", "gamma0", "gamma_sums", "reduced"):
-        assert np.array_equal(a[k], b[k]), k
-    for c in range(len(g.contigs)):
-        assert np.array_equal(ctx1.debug_alpha_hat(c), ctx2.debug_alpha_hat(c))
-    assert ctx1.stats()["mma_rounds"] == ctx2.stats()["mma_rounds"] and ctx1.stats()["mma_steps"] == ctx2.stats()["mma_steps"]
-    check_against(b, g.ref)
-    ctx1.close()
-    ctx2.close()
-
-
 @pytest.mark.parametrize("name", ["c1_2k", "c2_1500", "m17_800", "c4_twopop_1200", "ragged"])
 @pytest.mark.parametrize("G,fused", [(8, 0), (8, 1), (2, 0), (1, 1)])
 def test_two_tile_recursions_are_bitwise_the_one_tile_recursions(name, G, fused):
