@@ -217,6 +217,32 @@ int64_t smcpp_b200_obs_rows(const smcpp_b200_obs *o);
 float smcpp_b200_obs_last_ms(const smcpp_b200_obs *o);
 int smcpp_b200_obs_download(smcpp_b200_obs *o, int32_t *rows /* rows() x (1 + 3 npop) */);
 
+/*
+ * Several GPUs in ONE process (the drop-in case: `smc++ estimate` is a single Python process).  A multi handle owns one
+ * context per device, shards the contigs over them by longest processing time (contigs are independent HMMs, reference
+ * src/inference_manager.cpp:89-94: `#pragma omp parallel for` over hmms), drives each device from its own host thread and
+ * sums the packed statistics with ONE ncclAllReduce(ncclDouble, ncclSum) per E-step, in place in device memory (NCCL is
+ * bound at run time; a handle with one device never loads it).
+ * Replaces: InferenceManager::parallel_do (src/inference_manager.cpp:89-94) + the sums over HMMs of InferenceManager::Q /
+ *           loglik (:116-126, :174-177).
+ *   multi_set_contigs  derives the global key table (union over all contigs, std::map order) and uploads every shard;
+ *   multi_estep        pi / T / E as in smcpp_b200_estep (the library computes the eigensystems); per-contig outputs in the
+ *                      CALLER's contig order, key_present[C][K], reduced[1 + M + M*M + K*M] = the all-reduced statistics;
+ *   multi_context      the i-th device's context (options, statistics, smcpp_b200_q on that device's contigs).
+ */
+typedef struct smcpp_b200_multi smcpp_b200_multi;
+int smcpp_b200_multi_create(smcpp_b200_multi **out, const int *devices, int n_devices);
+void smcpp_b200_multi_destroy(smcpp_b200_multi *m);
+const char *smcpp_b200_multi_last_error(const smcpp_b200_multi *m); /* m may be NULL: error of the last failed create() */
+int smcpp_b200_multi_num_devices(const smcpp_b200_multi *m);
+int smcpp_b200_multi_context(smcpp_b200_multi *m, int i, smcpp_b200_ctx **ctx);
+int smcpp_b200_multi_set_contigs(smcpp_b200_multi *m, int n_contigs, const int32_t *const *obs, const int32_t *lengths, int npop);
+int smcpp_b200_multi_num_keys(const smcpp_b200_multi *m);
+int smcpp_b200_multi_get_keys(const smcpp_b200_multi *m, int32_t *keys /* K*3P */);
+int smcpp_b200_multi_get_shard(const smcpp_b200_multi *m, int device_index, int32_t *contigs /* or NULL */, int32_t *n);
+int smcpp_b200_multi_estep(smcpp_b200_multi *m, int M, const double *pi, const double *T, const double *E, double *ll,
+                           double *xisum, double *gamma0, double *gamma_sums, uint8_t *key_present, double *reduced);
+
 /* Diagnostics of the last estep(): see smcpp_b200_stats_t. */
 typedef struct smcpp_b200_stats_t {
     int32_t n_chunks;        /* chunks the contigs were split into */

@@ -46,6 +46,9 @@ SYMBOLS = [
     "smcpp_b200_reduced_device_ptr", "smcpp_b200_copy_reduced_to_device", "smcpp_b200_estep_device", "smcpp_b200_fetch", "smcpp_b200_get_stats",
     "smcpp_b200_fp64_peak", "smcpp_b200_stream", "smcpp_b200_debug_alpha_hat", "smcpp_b200_set_save_gamma",
     "smcpp_b200_fetch_gamma", "smcpp_b200_q", "smcpp_b200_set_statistics",
+    "smcpp_b200_multi_create", "smcpp_b200_multi_destroy", "smcpp_b200_multi_last_error", "smcpp_b200_multi_num_devices",
+    "smcpp_b200_multi_context", "smcpp_b200_multi_set_contigs", "smcpp_b200_multi_num_keys", "smcpp_b200_multi_get_keys",
+    "smcpp_b200_multi_get_shard", "smcpp_b200_multi_estep",
     "smcpp_b200_obs_create", "smcpp_b200_obs_destroy", "smcpp_b200_obs_last_error", "smcpp_b200_obs_upload", "smcpp_b200_obs_thin",
     "smcpp_b200_obs_bin", "smcpp_b200_obs_recode_monomorphic", "smcpp_b200_obs_compress", "smcpp_b200_obs_rows", "smcpp_b200_obs_last_ms",
     "smcpp_b200_obs_download", "smcpp_b200_obs_recode_nonseg", "smcpp_b200_obs_break_long_spans", "smcpp_b200_obs_piece_offsets",
@@ -86,6 +89,12 @@ def lib():
         L.smcpp_b200_obs_last_ms.argtypes = [ctypes.c_void_p]
         L.smcpp_b200_obs_destroy.restype = None
         L.smcpp_b200_obs_destroy.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_multi_last_error.restype = ctypes.c_char_p
+        L.smcpp_b200_multi_last_error.argtypes = [ctypes.c_void_p]
+        L.smcpp_b200_multi_destroy.restype = None
+        L.smcpp_b200_multi_destroy.argtypes = [ctypes.c_void_p]
+        for name in ("smcpp_b200_multi_num_keys", "smcpp_b200_multi_num_devices"):
+            getattr(L, name).argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -171,9 +180,9 @@ class Context:
                 self.set_option(k.strip(), float(v))
 
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             lib().smcpp_b200_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        self._h = ctypes.c_void_p()
 
     def __del__(self):
         try:
@@ -354,6 +363,79 @@ class Context:
         out = np.empty((L + 1, self.M), np.float32)
         self._check(lib().smcpp_b200_debug_alpha_hat(self._h, ctypes.c_int(contig), ptr(out, c_f32p)), "debug_alpha_hat")
         return out
+
+
+class MultiContext:
+    """Several GPUs in one process (include/smcpp_b200.h: smcpp_b200_multi_*): contigs sharded over the devices, one
+    in-library ncclAllReduce of the packed statistics per E-step."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(list(devices), np.int32)
+        self._h = ctypes.c_void_p()
+        if lib().smcpp_b200_multi_create(ctypes.byref(self._h), ptr(devs, c_i32p), ctypes.c_int(len(devs))):
+            raise RuntimeError("smcpp_b200_multi_create: " + lib().smcpp_b200_multi_last_error(None).decode())
+        self.devices = [int(d) for d in devs]
+        self.C = self.K = 0
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: " + lib().smcpp_b200_multi_last_error(self._h).decode())
+
+    def set_contigs(self, contigs, npop: int):
+        arrs = [np.ascontiguousarray(c, np.int32) for c in contigs]
+        C = len(arrs)
+        ptrs = (c_i32p * C)(*[ptr(a, c_i32p) for a in arrs])
+        lens = np.asarray([a.shape[0] for a in arrs], np.int32)
+        self._check(lib().smcpp_b200_multi_set_contigs(self._h, ctypes.c_int(C), ptrs, ptr(lens, c_i32p), ctypes.c_int(npop)), "multi_set_contigs")
+        self.C, self.npop = C, npop
+        self.K = lib().smcpp_b200_multi_num_keys(self._h)
+
+    @property
+    def keys(self):
+        k = np.empty((self.K, 3 * self.npop), np.int32)
+        self._check(lib().smcpp_b200_multi_get_keys(self._h, ptr(k, c_i32p)), "multi_get_keys")
+        return k
+
+    def shard(self, i: int):
+        n = ctypes.c_int32()
+        self._check(lib().smcpp_b200_multi_get_shard(self._h, ctypes.c_int(i), None, ctypes.byref(n)), "multi_get_shard")
+        out = np.empty(n.value, np.int32)
+        self._check(lib().smcpp_b200_multi_get_shard(self._h, ctypes.c_int(i), ptr(out, c_i32p), ctypes.byref(n)), "multi_get_shard")
+        return out
+
+    def context(self, i: int) -> "Context":
+        """A non-owning view of the i-th device's context (options, stats, q)."""
+        h = ctypes.c_void_p()
+        self._check(lib().smcpp_b200_multi_context(self._h, ctypes.c_int(i), ctypes.byref(h)), "multi_context")
+        c = Context.__new__(Context)
+        c._h, c._borrowed = h, True
+        c.K, c.npop, c.M = self.K, self.npop, 0
+        c.C = len(self.shard(i))
+        return c
+
+    def estep(self, pi, T, E) -> dict:
+        pi = np.ascontiguousarray(pi, np.float64); T = np.ascontiguousarray(T, np.float64); E = np.ascontiguousarray(E, np.float64)
+        M, K, C = pi.shape[0], self.K, self.C
+        if E.shape != (K, M) or T.shape != (M, M):
+            raise ValueError("shape mismatch: T must be [M,M], E must be [K,M]")
+        out = {"ll": np.empty(C), "xisum": np.empty((C, M, M)), "gamma0": np.empty((C, M)), "gamma_sums": np.empty((C, K, M)),
+               "key_present": np.empty((C, K), np.uint8), "reduced": np.empty(1 + M + M * M + K * M)}
+        self._check(lib().smcpp_b200_multi_estep(self._h, ctypes.c_int(M), ptr(pi, c_f64p), ptr(T, c_f64p), ptr(E, c_f64p),
+                                                 ptr(out["ll"], c_f64p), ptr(out["xisum"], c_f64p), ptr(out["gamma0"], c_f64p),
+                                                 ptr(out["gamma_sums"], c_f64p), ptr(out["key_present"], c_u8p),
+                                                 ptr(out["reduced"], c_f64p)), "multi_estep")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().smcpp_b200_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ObsPipeline:

@@ -68,7 +68,7 @@ def test_port_follows_the_reference_on_irregular_spectra(kind):
 @pytest.mark.gpu
 @pytest.mark.skipif(not refrun.available(), reason="oracle/_ref/ref_harness did not travel to this box")
 @pytest.mark.parametrize("kind", ["complex", "negative"])
-@pytest.mark.parametrize("M", [8, 33])
+@pytest.mark.parametrize("M", [8, 34])
 def test_device_follows_the_reference_on_irregular_spectra(kind, M):
     w = irregular_workload(kind, M=M, L=400 if M > 8 else 500)
     ref = refrun.run(w)
