@@ -348,7 +348,6 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "fused_recursions") ctx->rec.fused = value != 0;
     else if (n == "tiles") ctx->rec.tiles = value >= 2 ? 2 : 1;
     else if (n == "stats_streams") ctx->opt_stats_streams = value >= 2 ? 2 : 1;
-    else if (n == "stats_ctas") smcb::set_stats_ctas((int)value);            // experiment knob, process-wide
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;
     return 0;

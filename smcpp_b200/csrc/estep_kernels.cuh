@@ -188,7 +188,6 @@ void launch_stats_literal(const Model &m, const Plan &p, const Work &w, cudaStre
 void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
-void set_stats_ctas(int n);
 // M-step objective from the resident statistics (qfunc.cu); q[4 * (1 + D)]: per term the value and D derivatives
 void launch_q(int C, int M, int K, int D, const double *pi, const double *T, const double *E, const double *dpi, const double *dT,
               const double *dE, const uint8_t *present, const int32_t *key_nb, const double *gamma0, const double *xisum,

@@ -79,8 +79,7 @@ __device__ __forceinline__ void store_acc(double *sm, const double (&acc)[4][4][
 // output rows in global memory -- same code, same order, L2 instead of shared memory.
 constexpr int kS32MaxKeysSmem = 288;
 
-template <int MINB>
-__global__ void __launch_bounds__(kS32Warps * 32, MINB) k_stats32(Model m, Plan p, Work w, int gs_in_smem)
+__global__ void __launch_bounds__(kS32Warps * 32, 2) k_stats32(Model m, Plan p, Work w, int gs_in_smem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = m.K, NE = m.n_eig;
@@ -261,8 +260,7 @@ __global__ void __launch_bounds__(kS32Warps * 32, MINB) k_stats32(Model m, Plan 
 // unweighted.  Each warp keeps its R_e accumulator in shared memory (touched once per run) and G in registers.
 constexpr int kSEWarps = 4;
 
-template <int MINB>
-__global__ void __launch_bounds__(kSEWarps * 32, MINB) k_stats32e(Model m, Plan p, Work w)
+__global__ void __launch_bounds__(kSEWarps * 32, 2) k_stats32e(Model m, Plan p, Work w)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);                 // [kSEWarps][32*33]
@@ -735,9 +733,6 @@ void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t s
     else launch_statsT_impl<4>(m, p, w, st, st_runs);
 }
 
-static int g_stats_ctas = 2;    // experiment knob (process-wide, tools only): set_stats_ctas()
-void set_stats_ctas(int n) { g_stats_ctas = n == 3 ? 3 : 2; }
-
 size_t stats32_smem_bytes(const Model &m)
 {
     const size_t kk = m.K <= kS32MaxKeysSmem ? m.K : 0;
@@ -749,22 +744,13 @@ void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t s
 {
     const size_t smem = stats32_smem_bytes(m);
     static std::atomic<size_t> configured[kMaxDevices];
-    if (needs_smem_config(configured, smem)) {
-        cudaFuncSetAttribute(k_stats32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_stats32<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    // MINB = 3: 168 registers (a few spills) for three CTAs per SM instead of two (option "stats_ctas")
-    if (g_stats_ctas == 3) k_stats32<3><<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w, m.K <= kS32MaxKeysSmem ? 1 : 0);
-    else k_stats32<2><<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w, m.K <= kS32MaxKeysSmem ? 1 : 0);
+    if (needs_smem_config(configured, smem)) cudaFuncSetAttribute(k_stats32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_stats32<<<p.n_slabs, kS32Warps * 32, smem, st>>>(m, p, w, m.K <= kS32MaxKeysSmem ? 1 : 0);
     if (p.n_items > 0) {
         const size_t smem_e = ((size_t)kSEWarps * 32 * 33 + (size_t)kSEWarps * 32) * sizeof(double);
         static std::atomic<size_t> configured_e[kMaxDevices];
-        if (needs_smem_config(configured_e, smem_e)) {
-            cudaFuncSetAttribute(k_stats32e<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
-            cudaFuncSetAttribute(k_stats32e<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
-        }
-        if (g_stats_ctas == 3) k_stats32e<3><<<p.n_items, kSEWarps * 32, smem_e, st_runs>>>(m, p, w);
-        else k_stats32e<2><<<p.n_items, kSEWarps * 32, smem_e, st_runs>>>(m, p, w);
+        if (needs_smem_config(configured_e, smem_e)) cudaFuncSetAttribute(k_stats32e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+        k_stats32e<<<p.n_items, kSEWarps * 32, smem_e, st_runs>>>(m, p, w);
     }
 }
 
