@@ -176,6 +176,8 @@ int smcpp_b200_set_statistics(smcpp_b200_ctx *ctx, int M, const double *xisum /*
  * set_save_gamma(1) makes every following estep() also compute gamma[l][m] for l = 0..L of every contig (column 0 is
  * alpha_0 o beta_0; a column sums to the block's span); fetch_gamma copies one contig's [(L+1)][M] doubles to the host
  * (the reference's matrix is M x (L+1); the Python mirror returns the transposed view).
+ * set_save_gamma(2): every column is also divided by its sum on the device -- the normalisation `smc++ posterior` applies on
+ * the host before writing (reference smcpp/commands/posterior.py:104-106: g /= g.sum(axis=0)).
  */
 int smcpp_b200_set_save_gamma(smcpp_b200_ctx *ctx, int on);
 int smcpp_b200_fetch_gamma(smcpp_b200_ctx *ctx, int contig, double *out /* (L+1)*M */);

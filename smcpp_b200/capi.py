@@ -348,8 +348,9 @@ class Context:
         self._check(lib().smcpp_b200_stream(self._h, ctypes.byref(p)), "stream")
         return p.value or 0
 
-    def set_save_gamma(self, on: bool):
-        self._check(lib().smcpp_b200_set_save_gamma(self._h, ctypes.c_int(1 if on else 0)), "set_save_gamma")
+    def set_save_gamma(self, on, normalise: bool = False):
+        """on: keep every column of the posterior; normalise: columns divided by their sums on the device (`smc++ posterior`)."""
+        self._check(lib().smcpp_b200_set_save_gamma(self._h, ctypes.c_int((2 if normalise else 1) if on else 0)), "set_save_gamma")
 
     def fetch_gamma(self, contig: int) -> np.ndarray:
         """Posterior of one contig as [L+1, M] (the reference holds M x (L+1))."""

@@ -94,7 +94,7 @@ struct smcpp_b200_ctx {
     DevBuf<int32_t> d_span, d_span_id, d_span_list;
     DevBuf<double> m_pwtab, m_pwq, m_invdiff, w_gamma;
     DevBuf<int64_t> d_gcol_off;
-    bool save_gamma = false, gamma_valid = false;
+    bool save_gamma = false, gamma_valid = false, gamma_normalise = false;
     DevBuf<kcode_t> d_key;
     DevBuf<int64_t> d_blk_off, d_col_off;
     DevBuf<int32_t> d_chunk_off, d_slab_off, d_ch_contig, d_ch_start, d_ch_len, d_sl_contig, d_sl_start, d_sl_len;
@@ -848,7 +848,7 @@ static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, cons
     ctx->gamma_valid = false;
     if (ctx->save_gamma) {
         // full posterior decoding (reference saveGamma, src/hmm.cpp:48-49,147-148): M x (L+1) doubles per contig
-        launch_posterior(ctx->model(), p, w, ctx->w_gamma.p, ctx->d_gcol_off.p, ctx->n_sm, ctx->st);
+        launch_posterior(ctx->model(), p, w, ctx->w_gamma.p, ctx->d_gcol_off.p, ctx->gamma_normalise ? 1 : 0, ctx->n_sm, ctx->st);
         ctx->stats.kernel_launches += 2;
         ctx->gamma_valid = true;
     }
@@ -1291,6 +1291,7 @@ int smcpp_b200_set_save_gamma(smcpp_b200_ctx *ctx, int on)
 {
     if (!ctx) return 1;
     ctx->save_gamma = on != 0;
+    ctx->gamma_normalise = on == 2;      // 2: columns divided by their sums on the device (smcpp/commands/posterior.py:104-106)
     return 0;
 }
 

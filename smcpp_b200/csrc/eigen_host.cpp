@@ -7,12 +7,71 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 namespace smcb {
 namespace {
+
+// a few persistent helper threads for the per-key decompositions (process-wide, created on first use)
+class Pool {
+public:
+    static Pool &instance()
+    {
+        static Pool p;
+        return p;
+    }
+    int size() const { return (int)threads_.size(); }
+    void submit(std::function<void()> f)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+
+private:
+    Pool()
+    {
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int n = std::max(0, std::min(hw - 1, 7));
+        for (int i = 0; i < n; ++i)
+            threads_.emplace_back([this]() {
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lock(mu_);
+                        cv_.wait(lock, [this]() { return stop_ || !q_.empty(); });
+                        if (stop_ && q_.empty()) return;
+                        f = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false;
+};
 
 struct Mat {
     int n;
@@ -477,17 +536,24 @@ int host_eigensystems(int M, int K, int n_eig, const int32_t *eig_keys, const do
         for (int i = 0; i < M; ++i) d_scaled[(size_t)e * M + i] = de[i] / sc;
         if (cplx) cplx[e] = im > 0.0;
     };
-    const int hw = (int)std::thread::hardware_concurrency();
-    // (starting a thread costs ~0.1 ms, a 32 x 32 decomposition 0.3 ms: threads pay from 64 states on, 22 ms per key at 128)
-    const int nthreads = M < 64 ? 1 : std::max(1, std::min(n_eig, std::min(hw > 0 ? hw : 1, 16)));
-    if (nthreads <= 1) {
+    // helper threads are kept between calls (starting one costs ~0.1 ms, a 32 x 32 decomposition 0.3 ms)
+    const int workers = std::min(n_eig - 1, Pool::instance().size());
+    if (workers <= 0) {
         for (int e = 0; e < n_eig; ++e) one(e);
     } else {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nthreads; ++t)
-            pool.emplace_back([&, t]() { for (int e = t; e < n_eig; e += nthreads) one(e); });
-        for (int e = 0; e < n_eig; e += nthreads) one(e);
-        for (auto &th : pool) th.join();
+        std::atomic<int> next(0), pending(workers);
+        auto drain = [&]() { for (int e = next.fetch_add(1); e < n_eig; e = next.fetch_add(1)) one(e); };
+        std::mutex mu;
+        std::condition_variable cv;
+        for (int t = 0; t < workers; ++t)
+            Pool::instance().submit([&]() {
+                drain();
+                std::lock_guard<std::mutex> lock(mu);
+                if (--pending == 0) cv.notify_one();
+            });
+        drain();
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&]() { return pending.load() == 0; });
     }
     for (int e = 0; e < n_eig; ++e)
         if (rc[e]) {

@@ -185,7 +185,7 @@ void launch_check_backward(const Model &m, const Plan &p, const Work &w, double 
 void launch_stats(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);
 void launch_finalize(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
 void launch_stats_literal(const Model &m, const Plan &p, const Work &w, cudaStream_t st);
-void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st);
+void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int normalise, int n_sm, cudaStream_t st);
 void launch_gather_alpha(const Model &m, const Plan &p, const Work &w, int contig, float *out, int n_sm, cudaStream_t st);
 int stats_smem_bytes(const Model &m);
 // M-step objective from the resident statistics (qfunc.cu); q[4 * (1 + D)]: per term the value and D derivatives

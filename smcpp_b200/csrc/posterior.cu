@@ -16,7 +16,7 @@ namespace smcb {
 constexpr int kPostWarps = 4;
 
 template <int R>
-__global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, Work w, double *gamma, const int64_t *gcol_off)
+__global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, Work w, double *gamma, const int64_t *gcol_off, int normalise)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int M = m.M, Mp = m.Mp;
@@ -43,10 +43,19 @@ __global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, 
         if (l == 0) {   // alpha_hat_0 o beta_0, reference src/hmm.cpp:150
             const float *a0 = w.alpha + colbase * Mp;
             const double *b0 = w.beta_out + (size_t)p.chunk_off[t] * Mp;
+            double v0[R], tot = 0.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int j = lane + 32 * r;
-                if (j < M) out[j] = (double)a0[j] * b0[j];
+                v0[r] = j < M ? (double)a0[j] * b0[j] : 0.0;
+                tot += v0[r];
+            }
+            // normalise: every column divided by its sum, as `smc++ posterior` does on the host (smcpp/commands/posterior.py:104-106)
+            const double inv0 = normalise ? 1.0 / warp_sum(tot) : 1.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = lane + 32 * r;
+                if (j < M) out[j] = normalise ? v0[r] * inv0 : v0[r];
             }
             continue;
         }
@@ -65,10 +74,14 @@ __global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, 
                 part += v[r];
             }
             const double pp = warp_sum(part);
+            double tot = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { v[r] = v[r] / pp; tot += lane + 32 * r < M ? v[r] : 0.0; }
+            const double inv1 = normalise ? 1.0 / warp_sum(tot) : 1.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int j = lane + 32 * r;
-                if (j < M) out[j] = v[r] / pp;
+                if (j < M) out[j] = normalise ? v[r] * inv1 : v[r];
             }
             continue;
         }
@@ -128,10 +141,14 @@ __global__ void __launch_bounds__(kPostWarps * 32) k_posterior(Model m, Plan p, 
             }
             __syncwarp();
         }
+        double tot = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r] = fabs(C * acc[r]); tot += lane + 32 * r < M ? acc[r] : 0.0; }   // the reference takes |.| (src/hmm.cpp:116)
+        const double inv2 = normalise ? 1.0 / warp_sum(tot) : 1.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int j = lane + 32 * r;
-            if (j < M) out[j] = fabs(C * acc[r]);   // the reference takes |.| (src/hmm.cpp:116)
+            if (j < M) out[j] = normalise ? acc[r] * inv2 : acc[r];
         }
     }
 }
@@ -149,7 +166,7 @@ __global__ void k_setup_invdiff(Model m)
     }
 }
 
-void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int n_sm, cudaStream_t st)
+void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamma, const int64_t *gcol_off, int normalise, int n_sm, cudaStream_t st)
 {
     {
         const long n = (long)m.n_eig * m.Mp * m.Mp;
@@ -158,10 +175,10 @@ void launch_posterior(const Model &m, const Plan &p, const Work &w, double *gamm
     const size_t smem = (size_t)kPostWarps * 5 * m.Mp * sizeof(double);
     const int blocks = n_sm * 8;
     switch (m.Mp / 32) {
-    case 1: k_posterior<1><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;
-    case 2: k_posterior<2><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;
-    case 3: k_posterior<3><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;
-    default: k_posterior<4><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off); break;
+    case 1: k_posterior<1><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off, normalise); break;
+    case 2: k_posterior<2><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off, normalise); break;
+    case 3: k_posterior<3><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off, normalise); break;
+    default: k_posterior<4><<<blocks, kPostWarps * 32, smem, st>>>(m, p, w, gamma, gcol_off, normalise); break;
     }
 }
 

@@ -502,6 +502,15 @@ def test_posterior_decoding_against_port(name, opts):
         # the per-key sums are the column sums of the full posterior (src/hmm.cpp:125-128, 140-143)
         tot = got[1:].sum(0)
         assert relmax(tot, out["gamma_sums"][c].sum(0)) <= 1e-9
+    # the column normalisation of `smc++ posterior` (smcpp/commands/posterior.py:104-106) on the device
+    ctx.set_save_gamma(True, normalise=True)
+    ctx.estep(ref["pi"], ref["T"], ref["E"], ref)
+    for c, obs in enumerate(g.contigs):
+        o = port.hmm_estep(obs, ref, save_gamma=True)
+        want = o["gamma_full"] / o["gamma_full"].sum(1, keepdims=True)
+        got = ctx.fetch_gamma(c)
+        assert np.allclose(got.sum(1), 1.0, rtol=1e-13)
+        assert relmax(got, want) <= (1e-10 if opts.get("force_sequential") else 1e-6)
     ctx.set_save_gamma(False)
     ctx.estep(ref["pi"], ref["T"], ref["E"], ref)
     with pytest.raises(RuntimeError, match="save_gamma"):
