@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmcpp_b200.so")
+LIB_PATH = os.environ.get("SMCPP_B200_LIB") or os.path.join(_HERE, "libsmcpp_b200.so")   # (override: profiling builds, tools/)
 _lib = None
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)

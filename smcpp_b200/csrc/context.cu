@@ -347,6 +347,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "fwd_cached_keys") ctx->rec.cached_keys = std::max(0, std::min(4, (int)value));
     else if (n == "fused_recursions") ctx->rec.fused = value != 0;
     else if (n == "tiles") ctx->rec.tiles = value >= 2 ? 2 : 1;
+    else if (n == "carveout") smcb::set_recursion_carveout((int)value);      // process-wide tuning knob (tools)
     else if (n == "stats_streams") ctx->opt_stats_streams = value >= 2 ? 2 : 1;
     else return fail(ctx, "unknown option " + n);
     ctx->plan_valid = false;

@@ -178,6 +178,7 @@ void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, 
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st);
 int resident_warps_mma(int n_sm, int Mp, const RecOpts &o);
 bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o);
+void set_recursion_carveout(int pct);
 void launch_check_forward(const Model &m, const Plan &p, const Work &w, float tol0, float tol, cudaStream_t st);
 void launch_backward(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);
 void launch_check_backward(const Model &m, const Plan &p, const Work &w, double tol, cudaStream_t st);

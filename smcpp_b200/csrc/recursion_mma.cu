@@ -34,6 +34,11 @@ constexpr unsigned kAll = 0xffffffffu;
 #define SMCB_STREAM_PW 0
 #endif
 constexpr bool kStreamPw = SMCB_STREAM_PW != 0;   // d~^span rows: ld.global.nc.L1::no_allocate
+// Timing ablations for tools/ablate.sh (WRONG results, never in the product build): 1 = the float step reads one row of its
+// step matrix instead of 32, 2 = every DMMA of a GEMV reuses the first B fragment, 3 = the float step runs 4 rows instead of 32
+#ifndef SMCB_ABLATE
+#define SMCB_ABLATE 0
+#endif
 
 __device__ __forceinline__ int st_of(int q, int idx) { return 8 * (idx >> 1) + 2 * q + (idx & 1); }
 
@@ -59,7 +64,8 @@ __device__ __forceinline__ void gemv8(const double *F, const double (&v)[8 * NS]
     for (int kt = 0; kt < 8 * NS; ++kt)
 #pragma unroll
         for (int nt = 0; nt < 4 * NS; ++nt) {
-            const double b = kShared ? F[(kt * 4 * NS + nt) * 32 + lane] : __ldg(F + (kt * 4 * NS + nt) * 32 + lane);
+            const int fi = SMCB_ABLATE == 2 ? 0 : (kt * 4 * NS + nt);
+            const double b = kShared ? F[fi * 32 + lane] : __ldg(F + fi * 32 + lane);
             dmma(c[nt][0], c[nt][1], v[kt], b);
         }
 #pragma unroll
@@ -157,13 +163,13 @@ __device__ __forceinline__ void float_gemv(const float *A, const float *Ag, bool
 {
     constexpr int MP = 32 * NS, NI = 8 * NS;
 #pragma unroll(NS == 1 ? 8 : 2)
-    for (int i4 = 0; i4 < MP / 4; ++i4) {
+    for (int i4 = 0; i4 < (SMCB_ABLATE == 3 ? 1 : MP / 4); ++i4) {
         const float4 xv = xr[i4];
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx) {
             const float xi = cidx == 0 ? xv.x : cidx == 1 ? xv.y : cidx == 2 ? xv.z : xv.w;
             const f32x2 xx = pack2(xi, xi);
-            const size_t row = (size_t)(4 * i4 + cidx) * 4 * NI;
+            const size_t row = SMCB_ABLATE == 1 ? 0 : (size_t)(4 * i4 + cidx) * 4 * NI;
 #pragma unroll
             for (int h = 0; h < NS; ++h) {
                 f32x2x4 av;
@@ -784,19 +790,38 @@ bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o) { return
 // register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
 static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
 
+// Percent of the unified L1 / shared-memory array requested as shared memory.  The forward pass streams its float step
+// matrices through L1 (54 % hit rate), so the recursion kernels ask for no more shared memory than their resident CTAs
+// need (measured on C3: 50 % -> 40 %: forward 7.59 -> 7.49 ms; a 3-contig shard 50 % -> 25 %: 1.89 -> 1.84 ms).  Both
+// kernels must get the SAME carve-out, otherwise the second one waits for the SMs to drain.
+static int g_carveout = -1;     // -1 = automatic; option "carveout" pins it (process-wide, tools)
+void set_recursion_carveout(int pct) { g_carveout = pct < 0 ? -1 : (pct > 100 ? 100 : pct); }
+static int g_carveout_now = 50;
+
 template <typename KF>
 static void set_attrs(KF kernel, size_t smem)
 {
     // forward and backward kernels must be able to share an SM: the same shared-memory carve-out for every variant,
     // otherwise the second kernel waits for the SMs to drain and the two passes run back to back
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout_now);
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-static void configure_once()
+// blocks: CTAs per recursion kernel; smem_pair: dynamic shared memory of one forward + one backward CTA
+static void configure_once(int blocks, int n_sm, size_t smem_pair)
 {
-    static std::atomic<size_t> done[kMaxDevices];
-    if (!needs_smem_config(done, 1)) return;
+    int want = g_carveout;
+    if (want < 0) {
+        const int per_sm = (blocks + n_sm - 1) / n_sm;                       // resident CTAs of each kernel per SM
+        const size_t need = (size_t)per_sm * (smem_pair + 2 * 1024) + 1024;    // + the 1 KB the driver reserves per CTA
+        want = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+        if (want > 100) want = 100;
+    }
+    static std::atomic<int> configured[kMaxDevices];
+    std::atomic<int> &c = configured[current_device_slot()];
+    if (c.load(std::memory_order_relaxed) == want + 1) return;
+    c.store(want + 1, std::memory_order_relaxed);
+    g_carveout_now = want;
     set_attrs(k_forward_mma<1, kFragReg>, fwd_smem(1, kFragReg, 4));
     set_attrs(k_forward_mma<1, kFragShared>, fwd_smem(1, kFragShared, 4));
     set_attrs(k_backward_mma<1, kFragReg>, bwd_smem(1, kFragReg));
@@ -812,11 +837,21 @@ static void configure_once()
     set_attrs(k_recursions_mma<4, kFragGlobal>, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)));
 }
 
+static size_t smem_pair(const Model &m, const RecOpts &o, int warps, int n_sm)
+{
+    if (m.Mp == 32) {
+        const int frag = use_reg_frags(warps, n_sm) ? kFragReg : kFragShared;
+        return fwd_smem(1, frag, cached_keys(m, o)) + bwd_smem(1, frag);
+    }
+    if (m.Mp == 64) return fwd_smem(2, kFragShared, 0) + bwd_smem(2, kFragShared);
+    return fwd_smem(4, kFragGlobal, 0) + bwd_smem(4, kFragGlobal);
+}
+
 void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
-    configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     if (m.Mp == 32) {
         const int nkc = cached_keys(m, o);
         if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, G, nkc);
@@ -830,9 +865,9 @@ void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, 
 
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
-    configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     if (m.Mp == 32) {
         if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, G);
         else k_backward_mma<1, kFragShared><<<blocks, kMW * 32, bwd_smem(1, kFragShared), st>>>(m, p, w, G);
@@ -847,9 +882,9 @@ void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm,
 bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
     if (o.fused == 0 || !mma_forward_pays(p.n_chunks, n_sm, m.Mp, o)) return false;
-    configure_once();
     const int G = chunks_per_warp(p.n_chunks, n_sm, o);
     const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     const int grid = 2 * blocks;
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
     if (m.Mp == 32) {
