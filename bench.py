@@ -265,6 +265,7 @@ def main():
     ap.add_argument("--ref-full-steps", type=int, default=1, help="reference arm, --gpus 1: timed FULL-LENGTH steps (after 1 warm-up); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-config sweep block (C2, C4, C5-*)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = args.workload
@@ -375,6 +376,29 @@ def main():
     value = total_blocks * args.steps / t_res
     e2e = total_blocks * args.steps / t_e2e
 
+    # ---- weak-scaling companion (N > 1): EVERY rank takes the whole 22-contig workload (N x 22 contigs in the job), the
+    # way the path shards when there are more contigs than GPUs; the headline above stays the fixed 22-contig workload
+    weak = None
+    final_stats = ctx.stats() if contigs else {"n_chunks": 0, "fwd_sweeps": 0, "bwd_sweeps": 0}
+    if world > 1 and not args.no_weak:
+        ctx.close()
+        wc = [synth.make_contig(L, n, 1000 + c, P) for c in range(C)]
+        ctx = capi.Context(local_rank)
+        ctx.set_contigs(wc, P, model["keys"])
+        contigs, keep = wc, contigs
+        for _ in range(3):
+            step_resident()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_resident()
+        barrier()
+        tw = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak = {"scaling": "weak", "workload": f"{C} contigs x {L} blocks PER GPU ({world * C} contigs in the job)",
+                "value": world * total_blocks * args.steps / float(tw[0]), "unit": "blocks/s", "ms_per_step": 1e3 * float(tw[0]) / args.steps}
+        contigs = keep
+
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         rec_ms = float(np.mean(ms_rec)) if ms_rec else float("nan")
@@ -407,7 +431,8 @@ def main():
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
                               "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},
-            "loglik": ll_total, "loglik_allreduce_check_rel": abs(ll_total - ll_check) / abs(ll_check), "chunks": ctx.stats()["n_chunks"], "sweeps": [ctx.stats()["fwd_sweeps"], ctx.stats()["bwd_sweeps"]],
+            "weak_scaling": weak,
+            "loglik": ll_total, "loglik_allreduce_check_rel": abs(ll_total - ll_check) / abs(ll_check), "chunks": final_stats["n_chunks"], "sweeps": [final_stats["fwd_sweeps"], final_stats["bwd_sweeps"]],
         }
         if not args.no_cpu_baseline:
             # reference on the host cores (bounded sample) + the SAME sample through the GPU path with the default planner:

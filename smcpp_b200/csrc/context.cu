@@ -195,7 +195,7 @@ struct smcpp_b200_ctx {
         Plan p;
         p.n_contigs = C; p.n_chunks = n_chunks; p.n_slabs = n_slabs;
         p.chunk_blocks = plan_Lc; p.burn_in = plan_burn; p.slab_blocks = plan_slab;
-        p.burn_in_fwd = std::max(0, std::min(plan_burn, opt_burn_in_fwd + burn_in_fwd_adapt));
+        p.burn_in_fwd = std::max(0, opt_burn_in_fwd + burn_in_fwd_adapt);
         p.total_blocks = total;
         p.span = d_span.p; p.kcode = d_key.p; p.span_id = d_span_id.p;
         p.blk_off = d_blk_off.p; p.col_off = d_col_off.p; p.chunk_off = d_chunk_off.p; p.slab_off = d_slab_off.p;
@@ -1064,8 +1064,11 @@ static int complete_estep(smcpp_b200_ctx *ctx, F refetch)
             if (fwd_redone) ctx->burn_in_fwd_adapt += 128;
             if (bwd_redone) ctx->burn_in_adapt += 128;
         } else {
-            ctx->burn_in_adapt += std::max(cur, 256);
-            ctx->burn_in_fwd_adapt += std::max(ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt, 256);
+            // anything worse: one and a half times the current length, in 128-block notches (doubling overshoots: 128 states
+            // on the benchmark model fail at 512 blocks -- 8e-6 / 7e-8 -- and pass at 768 with 5e-7 / 3e-13; 1024 costs 15 % more)
+            auto grow = [](int len) { return std::max(256, ((len / 2 + 127) / 128) * 128); };
+            if (bwd_redone) ctx->burn_in_adapt += grow(cur);
+            if (fwd_redone) ctx->burn_in_fwd_adapt += grow(ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt);
         }
     }
     ctx->stats_valid = !gave_up;
