@@ -151,7 +151,7 @@ struct smcpp_b200_ctx {
     DevBuf<float> w_alpha, w_cnorm, w_start_used, w_end_alpha, w_end_alpha_prev;
     DevBuf<double> w_uvec, w_Ritem, w_ditem;
     DevBuf<double> w_bvec, w_ll_chunk, w_bstart_used, w_beta_out, w_beta_out_prev, w_Xpart, w_Rpart, w_dpart, w_gspart,
-        w_scratch, w_sums, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
+        w_scratch, w_sums, w_sums_part, o_ll, o_xisum, o_gamma0, o_gamma_sums, o_reduced;
     DevBuf<uint8_t> w_fwd_flag, w_bwd_flag, w_fwd_rerun;
     DevBuf<int> w_counters;
     PinBuf<int> h_counters;
@@ -214,7 +214,7 @@ struct smcpp_b200_ctx {
         w.ll_chunk = w_ll_chunk.p; w.bstart_used = w_bstart_used.p; w.beta_out = w_beta_out.p;
         w.beta_out_prev = w_beta_out_prev.p; w.fwd_flag = w_fwd_flag.p; w.bwd_flag = w_bwd_flag.p; w.fwd_rerun = w_fwd_rerun.p;
         w.counters = w_counters.p;
-        w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p; w.sums = w_sums.p;
+        w.Xpart = w_Xpart.p; w.Rpart = w_Rpart.p; w.dpart = w_dpart.p; w.gspart = w_gspart.p; w.scratch = w_scratch.p; w.sums = w_sums.p; w.sums_part = w_sums_part.p;
         w.Xlit = w_Xlit.p; w.gslit = w_gslit.p; w.lit_scratch = w_lit_scratch.p; w.nanpos = w_nanpos.p; w.poison = w_poison.p;
         w.ll = o_ll.p; w.xisum = o_xisum.p; w.gamma0 = o_gamma0.p; w.gamma_sums = o_gamma_sums.p; w.reduced = o_reduced.p;
         return w;
@@ -311,7 +311,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx)
     ctx->w_alpha.release(); ctx->w_cnorm.release(); ctx->w_start_used.release(); ctx->w_end_alpha.release();
     ctx->w_end_alpha_prev.release(); ctx->w_bvec.release(); ctx->w_ll_chunk.release(); ctx->w_bstart_used.release();
     ctx->w_beta_out.release(); ctx->w_beta_out_prev.release(); ctx->w_Xpart.release(); ctx->w_Rpart.release();
-    ctx->w_dpart.release(); ctx->w_gspart.release(); ctx->w_scratch.release(); ctx->w_sums.release(); ctx->o_ll.release();
+    ctx->w_dpart.release(); ctx->w_gspart.release(); ctx->w_scratch.release(); ctx->w_sums.release(); ctx->w_sums_part.release(); ctx->o_ll.release();
     ctx->o_xisum.release(); ctx->o_gamma0.release(); ctx->o_gamma_sums.release(); ctx->o_reduced.release();
     ctx->w_fwd_flag.release(); ctx->w_bwd_flag.release(); ctx->w_fwd_rerun.release(); ctx->w_counters.release(); ctx->h_counters.release();
     ctx->h_out.release();
@@ -810,6 +810,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     CU(ctx->w_gspart.ensure((size_t)ctx->n_slabs * K * Mp));
     CU(ctx->w_scratch.ensure((size_t)C * 2 * MM));
     CU(ctx->w_sums.ensure((size_t)C * (MM + (size_t)ctx->n_eig * MM + (size_t)ctx->n_eig * Mp + (size_t)K * Mp)));
+    CU(ctx->w_sums_part.ensure((size_t)C * reduce_parts() * (MM + (size_t)ctx->n_eig * MM + (size_t)ctx->n_eig * Mp + (size_t)K * Mp)));
     CU(ctx->o_ll.ensure(C));
     CU(ctx->o_xisum.ensure((size_t)C * M * M));
     CU(ctx->o_gamma0.ensure((size_t)C * M));
@@ -854,7 +855,7 @@ static void enqueue_stats_and_finalize(smcpp_b200_ctx *ctx, const Model &m, cons
         ctx->gamma_valid = true;
     }
     launch_finalize(m, p, w, ctx->st);
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 4;
     cudaEventRecord(ctx->ev[4], ctx->st);
     cudaMemcpyAsync(ctx->h_counters.p, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st);
 }

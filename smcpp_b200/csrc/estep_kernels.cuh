@@ -135,6 +135,7 @@ struct Work {
     double *gspart;          // [n_slabs][K][Mp]
     double *scratch;         // [C][2][Mp*Mp]  temporaries of k_finalize
     double *sums;            // [C][sum_stride] slab partials reduced per contig: X | R_e | D_e | gs
+    double *sums_part;       // [C][reduce_parts()][sum_stride] first level of that reduction
     double *Xlit;            // [n_slabs][Mp*Mp]       literal-path partials of X (irregular eigen keys only; else nullptr)
     double *gslit;           // [n_slabs][n_eig][Mp]   literal-path partials of the gamma sums of the eigen keys
     double *lit_scratch;     // [n_slabs][2][Mp*Mp]
@@ -156,6 +157,7 @@ void launch_forward(const Model &m, const Plan &p, const Work &w, int pass, cuda
 void launch_forward32(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);   // Mp == 32
 void launch_backward32(const Model &m, const Plan &p, const Work &w, int pass, cudaStream_t st);  // Mp == 32
 size_t sums_stride(const Model &m);
+int reduce_parts();
 int resident_warps32(int n_sm);
 void launch_stats32(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);          // Mp == 32
 void launch_stats64(const Model &m, const Plan &p, const Work &w, cudaStream_t st, cudaStream_t st_runs);          // Mp == 64
