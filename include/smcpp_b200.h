@@ -261,6 +261,7 @@ typedef struct smcpp_b200_stats_t {
     int32_t mma_rounds, mma_steps; /* tensor-path forward kernel: warp rounds and committed chunk-steps (efficiency = steps / (8 rounds)) */
     int32_t literal_keys;          /* eigen keys with an irregular spectrum (complex pair / negative eigenvalue) in the last estep():
                                       they -- and the whole E-step's chain, run sequentially -- follow the reference's literal formulas */
+    int32_t restarts;              /* pass 0 was run again with a doubled burn-in this many times (many boundaries failed: slowly mixing model) */
     int32_t converged;             /* 0: the repair sweeps hit max_sweeps with chunk boundaries still failing -- estep() returned an error */
 } smcpp_b200_stats_t;
 int smcpp_b200_get_stats(const smcpp_b200_ctx *ctx, smcpp_b200_stats_t *out);

@@ -29,7 +29,7 @@ class Stats(ctypes.Structure):
                 ("ms_stats", ctypes.c_float), ("ms_finalize", ctypes.c_float), ("ms_total", ctypes.c_float),
                 ("fwd_max_mismatch", ctypes.c_double), ("bwd_max_mismatch", ctypes.c_double),
                 ("ms_forward_only", ctypes.c_float), ("mma_rounds", ctypes.c_int32), ("mma_steps", ctypes.c_int32),
-                ("literal_keys", ctypes.c_int32), ("converged", ctypes.c_int32)]
+                ("literal_keys", ctypes.c_int32), ("restarts", ctypes.c_int32), ("converged", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -135,6 +135,7 @@ struct smcpp_b200_ctx {
     // ---- plan
     bool plan_valid = false;
     int plan_Lc = 0, plan_burn = 0, plan_slab = 0;
+    int64_t plan_maxL = 0;
     int n_chunks = 0, n_slabs = 0;
     int64_t n_cols = 0;
     std::vector<int32_t> chunk_off, slab_off;
@@ -543,6 +544,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     if (burn < 0) burn = 0;
     int64_t maxL = 0;
     for (int c = 0; c < ctx->C; ++c) maxL = std::max<int64_t>(maxL, ctx->blk_off[c + 1] - ctx->blk_off[c]);
+    ctx->plan_maxL = maxL;
     int Lc;
     if (ctx->opt_force_sequential || ctx->literal_mode) Lc = (int)maxL;
     else if (ctx->opt_chunk_blocks > 0) Lc = ctx->opt_chunk_blocks;
@@ -1018,6 +1020,30 @@ static int complete_estep(smcpp_b200_ctx *ctx, F refetch)
     CU(cudaGetLastError());
     if (!ctx->pending) return 0;
     ctx->pending = false;
+    // Many failed boundaries mean that the burn-in is far too short for this model (a slowly mixing chain): repairing them
+    // chunk by chunk would take as many dependent sweeps as the longest run of failed chunks (measured on a 51-state
+    // bottleneck model: 619 sweeps).  Lengthen the burn-in of the failing pass(es) -- doubling, the plan may change with
+    // it -- and run pass 0 again, fully parallel; the sweeps below then only see stragglers.  The longer burn-in stays in
+    // force for the following E-steps.
+    int restarts = 0;
+    while (!ctx->opt_force_sequential && !ctx->literal_mode && restarts < 8) {
+        const int nf = ctx->h_counters.p[0], nb = ctx->h_counters.p[1];
+        const int thr = std::max(8, ctx->n_chunks / 50);
+        if (nf <= thr && nb <= thr) break;
+        const int cur_f = ctx->opt_burn_in_fwd + ctx->burn_in_fwd_adapt, cur_b = ctx->opt_burn_in + ctx->burn_in_adapt;
+        if ((nf <= thr || cur_f >= ctx->plan_maxL) && (nb <= thr || cur_b >= ctx->plan_maxL)) break;
+        if (nf > thr) ctx->burn_in_fwd_adapt += std::max(cur_f, 256);
+        if (nb > thr) ctx->burn_in_adapt += std::max(cur_b, 256);
+        ++restarts;
+        const int launches = ctx->stats.kernel_launches;
+        if (run_estep(ctx, ctx->M, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, false)) return 1;
+        ctx->stats.kernel_launches += launches;
+        ctx->pending = false;
+        if (refetch()) return 1;
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+    }
+    ctx->stats.restarts = restarts;
     const Model m = ctx->model();
     const Plan p = ctx->plan();
     const Work w = ctx->work();
