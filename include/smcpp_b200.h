@@ -37,7 +37,7 @@ void smcpp_b200_destroy(smcpp_b200_ctx *ctx);
 const char *smcpp_b200_last_error(const smcpp_b200_ctx *ctx); /* ctx may be NULL: error of the last failed create() */
 
 /* Tuning knobs (optional).  name in {"chunk_blocks", "burn_in_blocks" (both passes), "burn_in_blocks_forward", "target_warps", "slab_blocks", "fwd_tol",
- * "fwd_tol_burn_in", "bwd_tol", "max_sweeps", "force_sequential", "mma_min_chunks", "force_mma_forward", "chunks_per_warp",
+ * "fwd_tol_burn_in", "bwd_tol", "max_sweeps", "max_restarts", "force_sequential", "mma_min_chunks", "force_mma_forward", "chunks_per_warp",
  * "fwd_cached_keys", "fused_recursions"} (all per context; the last three exist for tests / experiments).
  * Note on "fwd_tol_burn_in" (default 1e-6): the forward pass of a chunk starts from a burn-in over the preceding blocks and
  * is accepted when its float alpha_hat start agrees with the neighbour chunk's end to this relative tolerance -- the noise

@@ -125,6 +125,7 @@ struct smcpp_b200_ctx {
     // boundary -> 1.9e-7 in xi): re-run chunks are held to bitwise equality (reached after at most #chunks sweeps).
     double opt_fwd_tol = 0.0, opt_fwd_tol0 = 1e-6, opt_bwd_tol = 1e-10;
     int opt_max_sweeps = 1 << 30;
+    int opt_max_restarts = 8;       // re-runs of pass 0 with a doubled burn-in when many boundaries fail
     int opt_force_sequential = 0;
     int opt_force_mma_forward = 0;  // tests: take the tensor-path forward kernel even where mma_forward_pays() says no
     int opt_stats_streams = 2;      // 2: span-1 and span>1 statistics kernels on two streams
@@ -341,6 +342,7 @@ int smcpp_b200_set_option(smcpp_b200_ctx *ctx, const char *name, double value)
     else if (n == "fwd_tol_burn_in") ctx->opt_fwd_tol0 = value;
     else if (n == "bwd_tol") ctx->opt_bwd_tol = value;
     else if (n == "max_sweeps") ctx->opt_max_sweeps = std::max(1, (int)value);
+    else if (n == "max_restarts") ctx->opt_max_restarts = std::max(0, (int)value);
     else if (n == "force_sequential") ctx->opt_force_sequential = value != 0;
     else if (n == "force_mma_forward") ctx->opt_force_mma_forward = value != 0;
     else if (n == "mma_min_chunks") ctx->opt_mma_min_chunks = std::max(1, (int)value);
@@ -1026,7 +1028,7 @@ static int complete_estep(smcpp_b200_ctx *ctx, F refetch)
     // it -- and run pass 0 again, fully parallel; the sweeps below then only see stragglers.  The longer burn-in stays in
     // force for the following E-steps.
     int restarts = 0;
-    while (!ctx->opt_force_sequential && !ctx->literal_mode && restarts < 8) {
+    while (!ctx->opt_force_sequential && !ctx->literal_mode && restarts < ctx->opt_max_restarts) {
         const int nf = ctx->h_counters.p[0], nb = ctx->h_counters.p[1];
         const int thr = std::max(8, ctx->n_chunks / 50);
         if (nf <= thr && nb <= thr) break;

@@ -157,7 +157,7 @@ def test_golden_library_eigensystems(name):
 def test_short_burn_in_is_repaired_by_sweeps():
     # burn-in far too short: boundary checks must fail and the sweeps must restore the exact chain
     g = Golden("c2_1500")
-    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": 50, "burn_in_blocks": 2})
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": 50, "burn_in_blocks": 2, "max_restarts": 0})
     st = ctx.stats()
     assert st["fwd_redone"] > 0 and st["fwd_sweeps"] > 1
     assert st["bwd_redone"] > 0 and st["bwd_sweeps"] > 1
@@ -169,9 +169,23 @@ def test_short_burn_in_is_repaired_by_sweeps():
     ctx.close()
 
 
+def test_mass_failures_rerun_pass_zero_with_a_longer_burn_in():
+    """Many failed boundaries = the burn-in is far too short: pass 0 is run again with a doubled burn-in (fully parallel)
+    instead of one dependent sweep per failed chunk in a row; the longer burn-in stays for the next E-step."""
+    g = Golden("c2_1500")
+    ctx, out = run_ctx(g.contigs, g.npop, g.ref, {"chunk_blocks": 25, "burn_in_blocks": 2, "mma_min_chunks": 1})
+    st = ctx.stats()
+    assert st["restarts"] >= 1 and st["fwd_sweeps"] + st["bwd_sweeps"] <= 6
+    check_against(out, g.ref)
+    out2 = ctx.estep(g.ref["pi"], g.ref["T"], g.ref["E"], g.ref)
+    assert ctx.stats()["restarts"] == 0
+    check_against(out2, g.ref)
+    ctx.close()
+
+
 def test_zero_burn_in_degenerates_to_sequential_sweeps():
     g = Golden("c1_2k")
-    ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0}, keys=g.ref["keys"])
+    ctx, out = run_ctx([g.contigs[0][:400]], g.npop, g.ref, {"chunk_blocks": 40, "burn_in_blocks": 0, "max_restarts": 0}, keys=g.ref["keys"])
     seq = port.hmm_estep(g.contigs[0][:400], g.ref)
     st = ctx.stats()
     assert st["fwd_sweeps"] > 1 and st["bwd_sweeps"] > 1      # every boundary starts wrong and is repaired
@@ -367,7 +381,7 @@ def test_exhausted_repair_sweeps_are_an_error():
     """With boundaries still failing when max_sweeps is reached the results are wrong: estep() must say so (round 1 returned 0)."""
     g = Golden("c2_1500")
     ctx = capi.Context(0)
-    for k, v in {"chunk_blocks": 50, "burn_in_blocks": 0, "max_sweeps": 2}.items():
+    for k, v in {"chunk_blocks": 50, "burn_in_blocks": 0, "max_sweeps": 2, "max_restarts": 0}.items():
         ctx.set_option(k, v)
     ctx.set_contigs(g.contigs, g.npop)
     with pytest.raises(RuntimeError, match="max_sweeps"):
