@@ -454,6 +454,45 @@ int complex_inverse(int n, std::vector<std::complex<double>> &A, std::vector<std
 
 }  // namespace
 
+// the same elimination in real arithmetic (a real spectrum has real eigenvectors: a quarter of the complex flops)
+int real_inverse(int n, std::vector<double> &A, double *Inv)
+{
+    std::vector<int> piv(n);
+    for (int i = 0; i < n; ++i) piv[i] = i;
+    for (int k = 0; k < n; ++k) {
+        int best = k;
+        double bv = std::fabs(A[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            const double v = std::fabs(A[(size_t)i * n + k]);
+            if (v > bv) { bv = v; best = i; }
+        }
+        if (bv == 0.0) return 1;
+        if (best != k) {
+            for (int j = 0; j < n; ++j) std::swap(A[(size_t)k * n + j], A[(size_t)best * n + j]);
+            std::swap(piv[k], piv[best]);
+        }
+        const double pivv = A[(size_t)k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const double f = A[(size_t)i * n + k] / pivv;
+            A[(size_t)i * n + k] = f;
+            if (f != 0.0)
+                for (int j = k + 1; j < n; ++j) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+        }
+    }
+    std::vector<double> col(n);
+    for (int c = 0; c < n; ++c) {
+        for (int i = 0; i < n; ++i) col[i] = piv[i] == c ? 1.0 : 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < i; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
+        for (int i = n - 1; i >= 0; --i) {
+            for (int j = i + 1; j < n; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
+            col[i] /= A[(size_t)i * n + i];
+        }
+        for (int i = 0; i < n; ++i) Inv[(size_t)i * n + c] = col[i];
+    }
+    return 0;
+}
+
 int host_eig_real_general(int n, const double *A, double *P_r, double *Pinv_r, double *d_r, double *d_i, std::string *msg)
 {
     typedef std::complex<double> cd;
@@ -468,6 +507,24 @@ int host_eig_real_general(int n, const double *A, double *P_r, double *Pinv_r, d
     if (schur_vectors(H, V, d, e)) {
         if (msg) *msg = "QR iteration did not converge";
         return 1;
+    }
+    bool real_spectrum = true;
+    for (int j = 0; j < n; ++j) real_spectrum = real_spectrum && e[j] == 0.0;
+    if (real_spectrum) {
+        // real eigenvectors, unit 2-norm columns (as Eigen's EigenSolver::eigenvectors()), real inverse
+        std::vector<double> LUr((size_t)n * n);
+        for (int j = 0; j < n; ++j) {
+            double nrm = 0.0;
+            for (int i = 0; i < n; ++i) nrm += V(i, j) * V(i, j);
+            nrm = std::sqrt(nrm);
+            for (int i = 0; i < n; ++i) P_r[(size_t)i * n + j] = LUr[(size_t)i * n + j] = V(i, j) / nrm;
+        }
+        if (real_inverse(n, LUr, Pinv_r)) {
+            if (msg) *msg = "eigenvector matrix is singular";
+            return 1;
+        }
+        for (int i = 0; i < n; ++i) { d_r[i] = d[i]; d_i[i] = 0.0; }
+        return 0;
     }
     // complex eigenvector matrix, unit 2-norm columns (as Eigen's EigenSolver::eigenvectors())
     std::vector<cd> Pc((size_t)n * n), Pinv;
