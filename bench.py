@@ -421,7 +421,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
             "e2e": {"value": e2e, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "device_ms_per_step": e2e_stats.get("ms_total")},
-            "roofline": {"bound": "hbm", "kernel": "k_recursions_mma (forward + backward recursion in one launch, rank 0)", "achieved": ach,
+            "roofline": {"bound": "hbm", "kernel": "k_forward_mma || k_backward_mma (the two recursions, concurrent on two side streams, rank 0)", "achieved": ach,
                          "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          # dram__bytes_read + dram__bytes_write of that kernel / of all kernels of one E-step (ncu, profiles/)
                          "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
