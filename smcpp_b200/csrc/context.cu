@@ -114,7 +114,7 @@ struct smcpp_b200_ctx {
     int burn_in_fwd_adapt = 0;
     int opt_target_warps = 0;       // 0 = auto: one resident wave of the recursion kernels
     int n_sm = 148;
-    int opt_slab_blocks = 0;        // 0 = auto: up to 16384 blocks, but at least ~8 slabs per SM
+    int opt_slab_blocks = 0;        // 0 = auto: up to 16384 blocks, but at least ~2.5 slabs per SM
     // Forward boundaries are compared as FLOAT vectors.  Pass 0 compares a chunk's burn-in state with its neighbour's end
     // state: two float trajectories with different histories, which agree only to the accumulated rounding noise of the
     // chain (they usually merge bit for bit; the tail over ~10^4 boundaries of the benchmark model is 3.1e-7 of the largest
@@ -608,7 +608,7 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     // need enough slabs to fill the GPU (a single 10^6-block contig would get 61)
     int slab = ctx->opt_slab_blocks;
     if (slab <= 0) {
-        const int64_t per = ctx->total / ((int64_t)ctx->n_sm * 8);
+        const int64_t per = ctx->total * 2 / ((int64_t)ctx->n_sm * 5);     // r2, 3 x 10^6 blocks: 8192 -> 0.47 ms, 4096 -> 0.50, 2528 -> 0.53
         slab = (int)std::min<int64_t>(16384, std::max<int64_t>(2048, (per / 32) * 32));
     }
     const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M && ctx->plan_literal == ctx->literal_mode;
