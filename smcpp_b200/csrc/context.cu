@@ -608,8 +608,11 @@ static int make_plan(smcpp_b200_ctx *ctx, int M)
     // need enough slabs to fill the GPU (a single 10^6-block contig would get 61)
     int slab = ctx->opt_slab_blocks;
     if (slab <= 0) {
-        const int64_t per = ctx->total * 2 / ((int64_t)ctx->n_sm * 5);     // r2, 3 x 10^6 blocks: 8192 -> 0.47 ms, 4096 -> 0.50, 2528 -> 0.53
-        slab = (int)std::min<int64_t>(16384, std::max<int64_t>(2048, (per / 32) * 32));
+        // ~2.5 slabs per SM, as a power of two: a slab of 8192 blocks is exactly 2 MB of beta rows (one page per CTA).
+        // r2, 3 x 10^6 blocks: 8192 -> 0.47 ms, 16384 -> 0.49, 4096 -> 0.50, 8096 -> 0.53, 2528 -> 0.53
+        const double per = (double)ctx->total * 2.0 / ((double)ctx->n_sm * 5.0);
+        slab = 2048;
+        while (slab < 16384 && (double)slab * 1.41421356 < per) slab *= 2;
     }
     const bool same = ctx->plan_valid && ctx->plan_Lc == Lc && ctx->plan_slab == slab && ctx->M == M && ctx->plan_literal == ctx->literal_mode;
     ctx->plan_burn = burn;
