@@ -269,10 +269,11 @@ struct ObsBatch {          // (span, span id, code) of 8 consecutive blocks of t
 // forward and backward then run one after the other), shared memory (all warps of both kernels resident at once) or
 // global memory through the read-only path (M = 128: a fragment table is 128 KB).  The launcher picks.
 template <int NS, int FRAG>
-__device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int nkc, const int bid)
+__device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, const Work &w, const int Gw, const int nkc, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP, XS = MP + 4;
     constexpr int NF = FRAG == kFragReg ? 32 : 1;
+    const int G = Gw & 255, wpc = (Gw >> 8) ? (Gw >> 8) : kMW;       // chunks per warp, warps of a CTA that carry chunks (pack_gw)
     static_assert(FRAG != kFragReg || NS == 1, "register fragments need M <= 32");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sF_Pinv = reinterpret_cast<double *>(smem_raw);       // [MM] + [MM], used when FRAG == shared
@@ -311,7 +312,7 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
     const int M = m.M;
 
     // G (<= 8) chunks per warp: small inputs spread over more warps (rows n >= G of the MMA stay idle)
-    const int c = n < G ? (bid * kMW + warp) * G + n : p.n_chunks;
+    const int c = (n < G && warp < wpc) ? (bid * wpc + warp) * G + n : p.n_chunks;
     bool active = c < p.n_chunks;
     const int cc = active ? c : 0;
     const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
@@ -517,10 +518,11 @@ __device__ __forceinline__ void forward_mma_body(const Model &m, const Plan &p, 
 
 // =============================================== backward ==================================================
 template <int NS, int FRAG>
-__device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p, const Work &w, const int G, const int bid)
+__device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p, const Work &w, const int Gw, const int bid)
 {
     constexpr int MP = 32 * NS, NI = 8 * NS, NT = 4 * NS, MM = MP * MP;
     constexpr int NF = FRAG == kFragReg ? 32 : 1;
+    const int G = Gw & 255, wpc = (Gw >> 8) ? (Gw >> 8) : kMW;
     static_assert(FRAG != kFragReg || NS == 1, "register fragments need M <= 32");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Td fragments (span-1 rounds) are shared-resident unless everything is read from global memory (M = 128)
@@ -549,7 +551,7 @@ __device__ __forceinline__ void backward_mma_body(const Model &m, const Plan &p,
     __syncthreads();
     const int M = m.M;
 
-    const int c = n < G ? (bid * kMW + (tid >> 5)) * G + n : p.n_chunks;
+    const int c = (n < G && (tid >> 5) < wpc) ? (bid * wpc + (tid >> 5)) * G + n : p.n_chunks;
     bool active = c < p.n_chunks;
     const int cc = active ? c : 0;
     const int t = p.ch_contig[cc], s = p.ch_start[cc], len = p.ch_len[cc];
@@ -773,19 +775,32 @@ int resident_warps_mma(int n_sm, int Mp, const RecOpts &o)
 
 // chunks per warp: 8 when there are enough chunks to give every SM `want` warps, fewer otherwise
 // (RecOpts::force_G, option "chunks_per_warp", pins it: small inputs otherwise always run with G = 1)
-static int chunks_per_warp(int n_chunks, int n_sm, const RecOpts &o)
+static int chunks_per_warp(int n_chunks, int n_sm, int Mp, const RecOpts &o)
 {
     if (o.force_G == 1 || o.force_G == 2 || o.force_G == 4 || o.force_G == 8) return o.force_G;
-    const int want = n_sm * 2;
+    // 128 states: a chunk step is 64 x the work of a 32-state step and the burn-in is long, so a single contig offers few
+    // chunks; four of them per warp and one warp per SM beat two per warp (r2, 977 chunks: forward 47 ms with G = 4, 50 with
+    // G = 8, 77 with G = 2 -- no better than the one-chunk-per-warp kernel)
+    const int want = Mp == 128 ? n_sm : n_sm * 2, floor_G = Mp == 128 ? 4 : 1;
     int G = 8;
-    while (G > 1 && (n_chunks + G - 1) / G < want) G >>= 1;
+    while (G > floor_G && (n_chunks + G - 1) / G < want) G >>= 1;
     return G;
 }
+
+// Warps of a CTA that carry chunks (packed into the kernels' G argument).  Spreading few warps over more, emptier CTAs was
+// measured and lost: at 128 states the B fragments come from global memory, and the warps of one CTA share them in L1
+// (977 chunks, 4 per warp: 245 one-warp CTAs 71.7 ms forward, 62 full CTAs 47.2 ms).  Kept as a mechanism, always kMW.
+static int warps_per_cta(int, int) { return kMW; }
+static int pack_gw(int G, int wpc) { return G | (wpc << 8); }
 
 // The tensor-path forward kernel gives each chunk only 4 lanes for the float GEMV of the span-1 step; above 32 states
 // that only pays off when every warp has its full 8 chunks, otherwise the one-chunk-per-warp kernel is used
 // (the backward pass has no float step and always takes the tensor path).
-bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o) { return Mp == 32 || chunks_per_warp(n_chunks, n_sm, o) == 8; }
+bool mma_forward_pays(int n_chunks, int n_sm, int Mp, const RecOpts &o)
+{
+    const int G = chunks_per_warp(n_chunks, n_sm, Mp, o);
+    return Mp == 32 || G == 8 || (Mp == 128 && G >= 4 && n_chunks >= n_sm);
+}
 
 // register-resident fragments pay off while forward + backward (250 registers each) still fit on the GPU together
 static bool use_reg_frags(int warps, int n_sm) { return warps <= n_sm * 6; }
@@ -849,32 +864,32 @@ static size_t smem_pair(const Model &m, const RecOpts &o, int warps, int n_sm)
 
 void launch_forward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
-    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
-    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    const int G = chunks_per_warp(p.n_chunks, n_sm, m.Mp, o);
+    const int warps = (p.n_chunks + G - 1) / G, wpc = warps_per_cta(warps, n_sm), blocks = (warps + wpc - 1) / wpc, Gw = pack_gw(G, wpc);
     configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     if (m.Mp == 32) {
         const int nkc = cached_keys(m, o);
-        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, G, nkc);
-        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared, nkc), st>>>(m, p, w, G, nkc);
+        if (use_reg_frags(warps, n_sm)) k_forward_mma<1, kFragReg><<<blocks, kMW * 32, fwd_smem(1, kFragReg, nkc), st>>>(m, p, w, Gw, nkc);
+        else k_forward_mma<1, kFragShared><<<blocks, kMW * 32, fwd_smem(1, kFragShared, nkc), st>>>(m, p, w, Gw, nkc);
     } else if (m.Mp == 64) {
-        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared, 0), st>>>(m, p, w, G, 0);
+        k_forward_mma<2, kFragShared><<<blocks, kMW * 32, fwd_smem(2, kFragShared, 0), st>>>(m, p, w, Gw, 0);
     } else {
-        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal, 0), st>>>(m, p, w, G, 0);
+        k_forward_mma<4, kFragGlobal><<<blocks, kMW * 32, fwd_smem(4, kFragGlobal, 0), st>>>(m, p, w, Gw, 0);
     }
 }
 
 void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
-    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
-    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    const int G = chunks_per_warp(p.n_chunks, n_sm, m.Mp, o);
+    const int warps = (p.n_chunks + G - 1) / G, wpc = warps_per_cta(warps, n_sm), blocks = (warps + wpc - 1) / wpc, Gw = pack_gw(G, wpc);
     configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     if (m.Mp == 32) {
-        if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, G);
-        else k_backward_mma<1, kFragShared><<<blocks, kMW * 32, bwd_smem(1, kFragShared), st>>>(m, p, w, G);
+        if (use_reg_frags(warps, n_sm)) k_backward_mma<1, kFragReg><<<blocks, kMW * 32, bwd_smem(1, kFragReg), st>>>(m, p, w, Gw);
+        else k_backward_mma<1, kFragShared><<<blocks, kMW * 32, bwd_smem(1, kFragShared), st>>>(m, p, w, Gw);
     } else if (m.Mp == 64) {
-        k_backward_mma<2, kFragShared><<<blocks, kMW * 32, bwd_smem(2, kFragShared), st>>>(m, p, w, G);
+        k_backward_mma<2, kFragShared><<<blocks, kMW * 32, bwd_smem(2, kFragShared), st>>>(m, p, w, Gw);
     } else {
-        k_backward_mma<4, kFragGlobal><<<blocks, kMW * 32, bwd_smem(4, kFragGlobal), st>>>(m, p, w, G);
+        k_backward_mma<4, kFragGlobal><<<blocks, kMW * 32, bwd_smem(4, kFragGlobal), st>>>(m, p, w, Gw);
     }
 }
 
@@ -882,21 +897,21 @@ void launch_backward_mma(const Model &m, const Plan &p, const Work &w, int n_sm,
 bool launch_recursions_mma(const Model &m, const Plan &p, const Work &w, int n_sm, const RecOpts &o, cudaStream_t st)
 {
     if (o.fused == 0 || !mma_forward_pays(p.n_chunks, n_sm, m.Mp, o)) return false;
-    const int G = chunks_per_warp(p.n_chunks, n_sm, o);
-    const int warps = (p.n_chunks + G - 1) / G, blocks = (warps + kMW - 1) / kMW;
+    const int G = chunks_per_warp(p.n_chunks, n_sm, m.Mp, o);
+    const int warps = (p.n_chunks + G - 1) / G, wpc = warps_per_cta(warps, n_sm), blocks = (warps + wpc - 1) / wpc, Gw = pack_gw(G, wpc);
     configure_once(blocks, n_sm, smem_pair(m, o, warps, n_sm));
     const int grid = 2 * blocks;
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
     if (m.Mp == 32) {
         const int nkc = cached_keys(m, o);
         if (use_reg_frags(warps, n_sm))
-            k_recursions_mma<1, kFragReg><<<grid, kMW * 32, mx(fwd_smem(1, kFragReg, nkc), bwd_smem(1, kFragReg)), st>>>(m, p, w, G, nkc, blocks);
+            k_recursions_mma<1, kFragReg><<<grid, kMW * 32, mx(fwd_smem(1, kFragReg, nkc), bwd_smem(1, kFragReg)), st>>>(m, p, w, Gw, nkc, blocks);
         else
-            k_recursions_mma<1, kFragShared><<<grid, kMW * 32, mx(fwd_smem(1, kFragShared, nkc), bwd_smem(1, kFragShared)), st>>>(m, p, w, G, nkc, blocks);
+            k_recursions_mma<1, kFragShared><<<grid, kMW * 32, mx(fwd_smem(1, kFragShared, nkc), bwd_smem(1, kFragShared)), st>>>(m, p, w, Gw, nkc, blocks);
     } else if (m.Mp == 64) {
-        k_recursions_mma<2, kFragShared><<<grid, kMW * 32, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)), st>>>(m, p, w, G, 0, blocks);
+        k_recursions_mma<2, kFragShared><<<grid, kMW * 32, mx(fwd_smem(2, kFragShared, 0), bwd_smem(2, kFragShared)), st>>>(m, p, w, Gw, 0, blocks);
     } else {
-        k_recursions_mma<4, kFragGlobal><<<grid, kMW * 32, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)), st>>>(m, p, w, G, 0, blocks);
+        k_recursions_mma<4, kFragGlobal><<<grid, kMW * 32, mx(fwd_smem(4, kFragGlobal, 0), bwd_smem(4, kFragGlobal)), st>>>(m, p, w, Gw, 0, blocks);
     }
     return true;
 }
