@@ -48,6 +48,36 @@ def test_built_for_sm100a():
     assert "sm_100a" in out, out
 
 
+_SASS_DUMP = []
+
+
+def _sass(function_substring):
+    import subprocess
+    if not _SASS_DUMP:
+        _SASS_DUMP.append(subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout)
+    body, keep = [], False
+    for line in _SASS_DUMP[0].splitlines():
+        if "Function :" in line:
+            keep = function_substring in line
+        elif keep:
+            body.append(line)
+    return "\n".join(body)
+
+
+@pytest.mark.parametrize("kernel,mnemonics", [
+    ("k_stats32ENS", ["DMMA.8x8x4", "LDGSTS", "MUFU.RCP64H"]),      # FP64 tensor path, cp.async operand ring, branch-free reciprocal
+    ("k_stats32eENS", ["DMMA.8x8x4", "LDGSTS"]),
+    ("k_forward_mmaILi1ELi1E", ["DMMA.8x8x4", "FFMA2"]),           # tensor-path recursion with the packed float step
+    ("k_backward_mmaILi1ELi1E", ["DMMA.8x8x4"]),
+])
+def test_hot_kernels_contain_the_instructions_the_design_names(kernel, mnemonics):
+    """The shipped cubin is what DESIGN.md describes (guards against a build that silently lost a code path)."""
+    sass = _sass(kernel)
+    assert sass, f"{kernel} not found in {capi.LIB_PATH}"
+    for mn in mnemonics:
+        assert mn in sass, f"{mn} missing from {kernel}"
+
+
 def test_header_is_valid_c99_and_a_plain_c_consumer_links(tmp_path):
     """examples/cabi_estep.c: strict C99 against include/smcpp_b200.h, linked to the in-tree library."""
     import subprocess
