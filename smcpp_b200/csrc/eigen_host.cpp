@@ -81,10 +81,22 @@ struct Mat {
     double operator()(int i, int j) const { return a[(size_t)i * n + j]; }
 };
 
-void hessenberg(Mat &H, Mat &V)
+// The accumulated transformation: element (i, j) at a[j * n + i], so that the loops over i below (one column of V at a time,
+// or two / three adjacent columns of the QR sweep) run over contiguous memory and vectorise.  Element-wise the arithmetic and
+// its order are those of the row-major version: results are bit-identical.
+struct MatT {
+    int n;
+    std::vector<double> a;
+    explicit MatT(int n_) : n(n_), a((size_t)n_ * n_, 0.0) {}
+    double &operator()(int i, int j) { return a[(size_t)j * n + i]; }
+    double operator()(int i, int j) const { return a[(size_t)j * n + i]; }
+    double *col(int j) { return a.data() + (size_t)j * n; }
+};
+
+void hessenberg(Mat &H, MatT &V)
 {
     const int n = H.n, low = 0, high = n - 1;
-    std::vector<double> ort(n, 0.0);
+    std::vector<double> ort(n, 0.0), fbuf(n, 0.0);
     for (int m = low + 1; m <= high - 1; ++m) {
         double scale = 0.0;
         for (int i = m; i <= high; ++i) scale += std::fabs(H(i, m - 1));
@@ -98,17 +110,44 @@ void hessenberg(Mat &H, Mat &V)
         if (ort[m] > 0) g = -g;
         h -= ort[m] * g;
         ort[m] -= g;
-        for (int j = m; j < n; ++j) {
-            double f = 0.0;
-            for (int i = high; i >= m; --i) f += ort[i] * H(i, j);
-            f /= h;
-            for (int i = m; i <= high; ++i) H(i, j) -= f * ort[i];
+        {
+            // f_j = sum_i ort_i H(i, j) for all j at once (i descending as before, j contiguous)
+            double *__restrict fj = fbuf.data();
+            for (int j = m; j < n; ++j) fj[j] = 0.0;
+            for (int i = high; i >= m; --i) {
+                const double oi = ort[i];
+                const double *__restrict hr = &H(i, 0);
+                for (int j = m; j < n; ++j) fj[j] += oi * hr[j];
+            }
+            for (int j = m; j < n; ++j) fj[j] /= h;
+            for (int i = m; i <= high; ++i) {
+                const double oi = ort[i];
+                double *__restrict hr = &H(i, 0);
+                for (int j = m; j < n; ++j) hr[j] -= fj[j] * oi;
+            }
         }
-        for (int i = 0; i <= high; ++i) {
-            double f = 0.0;
-            for (int j = high; j >= m; --j) f += ort[j] * H(i, j);
-            f /= h;
-            for (int j = m; j <= high; ++j) H(i, j) -= f * ort[j];
+        {
+            // four rows at a time: four independent summation chains instead of one (each in its original order)
+            int i = 0;
+            for (; i + 3 <= high; i += 4) {
+                double *__restrict h0 = &H(i, 0), *__restrict h1 = &H(i + 1, 0), *__restrict h2 = &H(i + 2, 0), *__restrict h3 = &H(i + 3, 0);
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+                for (int j = high; j >= m; --j) {
+                    const double o = ort[j];
+                    f0 += o * h0[j]; f1 += o * h1[j]; f2 += o * h2[j]; f3 += o * h3[j];
+                }
+                f0 /= h; f1 /= h; f2 /= h; f3 /= h;
+                for (int j = m; j <= high; ++j) {
+                    const double o = ort[j];
+                    h0[j] -= f0 * o; h1[j] -= f1 * o; h2[j] -= f2 * o; h3[j] -= f3 * o;
+                }
+            }
+            for (; i <= high; ++i) {
+                double f = 0.0;
+                for (int j = high; j >= m; --j) f += ort[j] * H(i, j);
+                f /= h;
+                for (int j = m; j <= high; ++j) H(i, j) -= f * ort[j];
+            }
         }
         ort[m] *= scale;
         H(m, m - 1) = scale * g;
@@ -118,11 +157,29 @@ void hessenberg(Mat &H, Mat &V)
     for (int m = high - 1; m >= low + 1; --m) {
         if (H(m, m - 1) == 0.0) continue;
         for (int i = m + 1; i <= high; ++i) ort[i] = H(i, m - 1);
-        for (int j = m; j <= high; ++j) {
-            double g = 0.0;
-            for (int i = m; i <= high; ++i) g += ort[i] * V(i, j);
-            g = (g / ort[m]) / H(m, m - 1);
-            for (int i = m; i <= high; ++i) V(i, j) += g * ort[i];
+        {
+            const double om = ort[m], hm = H(m, m - 1);
+            int j = m;
+            for (; j + 3 <= high; j += 4) {                       // four columns at a time (independent summation chains)
+                double *__restrict v0 = V.col(j), *__restrict v1 = V.col(j + 1), *__restrict v2 = V.col(j + 2), *__restrict v3 = V.col(j + 3);
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                for (int i = m; i <= high; ++i) {
+                    const double o = ort[i];
+                    g0 += o * v0[i]; g1 += o * v1[i]; g2 += o * v2[i]; g3 += o * v3[i];
+                }
+                g0 = (g0 / om) / hm; g1 = (g1 / om) / hm; g2 = (g2 / om) / hm; g3 = (g3 / om) / hm;
+                for (int i = m; i <= high; ++i) {
+                    const double o = ort[i];
+                    v0[i] += g0 * o; v1[i] += g1 * o; v2[i] += g2 * o; v3[i] += g3 * o;
+                }
+            }
+            for (; j <= high; ++j) {
+                double *__restrict vc = V.col(j);
+                double g = 0.0;
+                for (int i = m; i <= high; ++i) g += ort[i] * vc[i];
+                g = (g / om) / hm;
+                for (int i = m; i <= high; ++i) vc[i] += g * ort[i];
+            }
         }
     }
 }
@@ -145,7 +202,7 @@ inline void cdiv(double xr, double xi, double yr, double yi, double &zr, double 
 
 // H upper Hessenberg (destroyed: becomes quasi-triangular T, then holds the triangular eigenvectors),
 // V accumulates; on return the columns of V are the (real / real+imag pair) eigenvectors.
-int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e)
+int schur_vectors(Mat &H, MatT &V, std::vector<double> &d, std::vector<double> &e)
 {
     const int nn = H.n, low = 0, high = nn - 1;
     int n = nn - 1;
@@ -201,10 +258,13 @@ int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e
                     H(i, n - 1) = q * z + p * H(i, n);
                     H(i, n) = q * H(i, n) - p * z;
                 }
-                for (int i = low; i <= high; ++i) {
-                    z = V(i, n - 1);
-                    V(i, n - 1) = q * z + p * V(i, n);
-                    V(i, n) = q * V(i, n) - p * z;
+                {
+                    double *__restrict va = V.col(n - 1), *__restrict vb = V.col(n);
+                    for (int i = low; i <= high; ++i) {
+                        const double zz = va[i];
+                        va[i] = q * zz + p * vb[i];
+                        vb[i] = q * vb[i] - p * zz;
+                    }
                 }
             } else {
                 d[n - 1] = x + p;
@@ -288,14 +348,24 @@ int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e
                     z = r / s;
                     q /= p;
                     r /= p;
-                    for (int j = k; j < nn; ++j) {
-                        p = H(k, j) + q * H(k + 1, j);
+                    {
+                        double *__restrict h0 = &H(k, 0), *__restrict h1 = &H(k + 1, 0);
                         if (notlast) {
-                            p += r * H(k + 2, j);
-                            H(k + 2, j) -= p * z;
+                            double *__restrict h2 = &H(k + 2, 0);
+                            for (int j = k; j < nn; ++j) {
+                                double pp = h0[j] + q * h1[j];
+                                pp += r * h2[j];
+                                h2[j] -= pp * z;
+                                h0[j] -= pp * x;
+                                h1[j] -= pp * y;
+                            }
+                        } else {
+                            for (int j = k; j < nn; ++j) {
+                                const double pp = h0[j] + q * h1[j];
+                                h0[j] -= pp * x;
+                                h1[j] -= pp * y;
+                            }
                         }
-                        H(k, j) -= p * x;
-                        H(k + 1, j) -= p * y;
                     }
                     for (int i = 0; i <= std::min(n, k + 3); ++i) {
                         p = x * H(i, k) + y * H(i, k + 1);
@@ -306,14 +376,24 @@ int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e
                         H(i, k) -= p;
                         H(i, k + 1) -= p * q;
                     }
-                    for (int i = low; i <= high; ++i) {
-                        p = x * V(i, k) + y * V(i, k + 1);
+                    {
+                        double *__restrict v0 = V.col(k), *__restrict v1 = V.col(k + 1);
                         if (notlast) {
-                            p += z * V(i, k + 2);
-                            V(i, k + 2) -= p * r;
+                            double *__restrict v2 = V.col(k + 2);
+                            for (int i = low; i <= high; ++i) {
+                                double pp = x * v0[i] + y * v1[i];
+                                pp += z * v2[i];
+                                v2[i] -= pp * r;
+                                v0[i] -= pp;
+                                v1[i] -= pp * q;
+                            }
+                        } else {
+                            for (int i = low; i <= high; ++i) {
+                                const double pp = x * v0[i] + y * v1[i];
+                                v0[i] -= pp;
+                                v1[i] -= pp * q;
+                            }
                         }
-                        V(i, k) -= p;
-                        V(i, k + 1) -= p * q;
                     }
                 }
             }
@@ -402,12 +482,20 @@ int schur_vectors(Mat &H, Mat &V, std::vector<double> &d, std::vector<double> &e
         }
     }
     // back-transform with the accumulated orthogonal matrix
-    for (int j = nn - 1; j >= low; --j)
-        for (int i = low; i <= high; ++i) {
-            z = 0.0;
-            for (int k = low; k <= std::min(j, high); ++k) z += V(i, k) * H(k, j);
-            V(i, j) = z;
+    {
+        std::vector<double> acc(nn);
+        for (int j = nn - 1; j >= low; --j) {
+            double *__restrict out = acc.data();
+            for (int i = low; i <= high; ++i) out[i] = 0.0;
+            for (int k = low; k <= std::min(j, high); ++k) {          // k ascending per element, as before
+                const double hk = H(k, j);
+                const double *__restrict vk = V.col(k);
+                for (int i = low; i <= high; ++i) out[i] += vk[i] * hk;
+            }
+            double *__restrict vj = V.col(j);
+            for (int i = low; i <= high; ++i) vj[i] = out[i];
         }
+    }
     return 0;
 }
 
@@ -479,16 +567,27 @@ int real_inverse(int n, std::vector<double> &A, double *Inv)
                 for (int j = k + 1; j < n; ++j) A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
         }
     }
-    std::vector<double> col(n);
-    for (int c = 0; c < n; ++c) {
-        for (int i = 0; i < n; ++i) col[i] = piv[i] == c ? 1.0 : 0.0;
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < i; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
-        for (int i = n - 1; i >= 0; --i) {
-            for (int j = i + 1; j < n; ++j) col[i] -= A[(size_t)i * n + j] * col[j];
-            col[i] /= A[(size_t)i * n + i];
+    // all n right-hand sides at once: X(i, :) -= A(i, j) X(j, :) with the columns contiguous (per element the same
+    // operations in the same order as one column at a time)
+    double *__restrict X = Inv;
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < n; ++c) X[(size_t)i * n + c] = piv[i] == c ? 1.0 : 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) {
+            const double a = A[(size_t)i * n + j];
+            const double *__restrict xj = X + (size_t)j * n;
+            double *__restrict xi = X + (size_t)i * n;
+            for (int c = 0; c < n; ++c) xi[c] -= a * xj[c];
         }
-        for (int i = 0; i < n; ++i) Inv[(size_t)i * n + c] = col[i];
+    for (int i = n - 1; i >= 0; --i) {
+        double *__restrict xi = X + (size_t)i * n;
+        for (int j = i + 1; j < n; ++j) {
+            const double a = A[(size_t)i * n + j];
+            const double *__restrict xj = X + (size_t)j * n;
+            for (int c = 0; c < n; ++c) xi[c] -= a * xj[c];
+        }
+        const double dd = A[(size_t)i * n + i];
+        for (int c = 0; c < n; ++c) xi[c] /= dd;
     }
     return 0;
 }
@@ -496,7 +595,8 @@ int real_inverse(int n, std::vector<double> &A, double *Inv)
 int host_eig_real_general(int n, const double *A, double *P_r, double *Pinv_r, double *d_r, double *d_i, std::string *msg)
 {
     typedef std::complex<double> cd;
-    Mat H(n), V(n);
+    Mat H(n);
+    MatT V(n);
     std::copy(A, A + (size_t)n * n, H.a.begin());
     std::vector<double> d(n, 0.0), e(n, 0.0);
     if (n == 1) {
@@ -609,6 +709,13 @@ int host_eigensystems(int M, int K, int n_eig, const int32_t *eig_keys, const do
                 if (--pending == 0) cv.notify_one();
             });
         drain();
+        // the helpers finish within a decomposition's time of this thread: poll briefly before sleeping on the condition
+        // variable (a sleep + wake-up costs ~50 us of a ~200 us call)
+        for (int spin = 0; spin < 200000 && pending.load(std::memory_order_acquire) != 0; ++spin) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
         std::unique_lock<std::mutex> lock(mu);
         cv.wait(lock, [&]() { return pending.load() == 0; });
     }
