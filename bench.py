@@ -196,6 +196,19 @@ def sweep_block(capi, device, hbm_peak, fp64_peak, steps=5):
     return res
 
 
+def scaling_limiter(shards, st, wall_ms, device_ms):
+    """Rank 0's share of the strong-scaling loss: every chunk repeats `burn-in` blocks of its predecessor (forward 384 by
+    default, backward `burn_in_blocks`), the largest shard sets the pace, and the host works ~0.3 ms per step."""
+    sizes = [len(s) for s in shards]
+    chunk = int(st.get("chunk_blocks", 0) or 0)
+    burn_b = int(st.get("burn_in_blocks", 0) or 0)
+    burn_f = min(384, burn_b) if burn_b else 0
+    return {"rank0_contigs": sizes[0], "contigs_per_rank": sizes, "balance": (sum(sizes) / len(sizes)) / max(sizes) if max(sizes) else None,
+            "rank0_chunks": int(st.get("n_chunks", 0) or 0), "chunk_blocks": chunk, "burn_in_blocks": {"forward_default": burn_f, "backward": burn_b},
+            "redundant_step_share": {"forward": burn_f / (chunk + burn_f) if chunk else None, "backward": burn_b / (chunk + burn_b) if chunk else None},
+            "host_ms_per_step": wall_ms - device_ms if device_ms == device_ms else None}
+
+
 def measured_traffic(cfg, world):
     """dram__bytes_read + dram__bytes_write per E-step from the committed ncu capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -431,6 +444,9 @@ def main():
             "roofline_fp64": {"bound": "fp64 fma", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
                               "alg_flops_per_block": alg_flops_per_block(M), "estep_device_ms": tot_ms,
                               "peak_source": "smcpp_b200_fp64_peak (DFMA loop, CUDA events)"},
+            # what limits strong scaling, from rank 0's plan: redundant burn-in steps of its chunks,
+            # contig imbalance, host time per step (eigensolver, launches, all-reduce)
+            "scaling_limiter": scaling_limiter(parallel.shard_contigs([L] * C, world), final_stats, 1e3 * t_res / args.steps, tot_ms),
             "weak_scaling": weak,
             "loglik": ll_total, "loglik_allreduce_check_rel": abs(ll_total - ll_check) / abs(ll_check), "chunks": final_stats["n_chunks"], "sweeps": [final_stats["fwd_sweeps"], final_stats["bwd_sweeps"]],
         }
